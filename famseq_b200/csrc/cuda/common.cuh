@@ -1,0 +1,67 @@
+// common.cuh -- pieces shared by the three method kernels: the per-run constant block, the
+// individual-only posterior + LRC gate every method starts with (family.cpp:1405-1499, :767-789) and
+// the arg-max of get_postRlt (family.cpp:636-665).
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace famseq {
+
+constexpr int FS_MAX_MEMBERS = 128;
+enum : int { K_TAB_AUTO = 0, K_TAB_XF = 1, K_TAB_XM = 2 }; // same values as host TableKind
+
+// Passed by value as a __grid_constant__ kernel parameter: lives in the constant bank, so table
+// entries become direct constant operands of the FP64 instructions.
+struct RunConstants {
+    double tab[3][27];  // [TAB_AUTO|TAB_XF|TAB_XM][g*9 + mother*3 + father]
+    double prior[4][3]; // genoProbN, genoProbK, genoProbXN, genoProbXK
+    double lrc;         // -LRC
+    int32_t n, s;
+    // unseq_fail[flags & 3]: some UNSEQUENCED member's prior row sums to <= 0 for this (Known, chrX)
+    // combination, i.e. calPostProbSingle would return false for every such variant.
+    uint8_t unseq_fail[4];
+    uint8_t col_male[FS_MAX_MEMBERS]; // gender == 1 of the member behind each input column
+    uint8_t pad[4];
+};
+
+struct BatchPtrs {
+    const double *lk;     // [V][S][3]
+    const uint8_t *flags; // [V] or nullptr
+    double *post;         // [V][S][3]
+    double *single;       // [V][S][3]
+    uint8_t *gt;          // [V][S]
+    uint8_t *status;      // [V]
+    int64_t V;
+};
+
+// Prior pair of one variant: `a` for females and for everybody on autosomes, `m` for males.
+struct VariantPriors {
+    double a[3], m[3];
+};
+
+__device__ __forceinline__ VariantPriors select_priors(const RunConstants &C, unsigned flag) {
+    const int known = flag & 1, chrx = (flag >> 1) & 1;
+    VariantPriors p;
+#pragma unroll
+    for (int g = 0; g < 3; g++) {
+        p.a[g] = known ? C.prior[1][g] : C.prior[0][g];
+        p.m[g] = chrx ? (known ? C.prior[3][g] : C.prior[2][g]) : p.a[g];
+    }
+    return p;
+}
+
+// a[g] for a runtime g without turning the array into local memory
+__device__ __forceinline__ double pick3(const double (&a)[3], int g) { return g == 0 ? a[0] : (g == 1 ? a[1] : a[2]); }
+
+// get_postRlt: strict '<' starting from -1, so the first maximum wins and NaN rows give -1 (255).
+__device__ __forceinline__ uint8_t call_genotype(double p0, double p1, double p2) {
+    double big = -1.0;
+    int arg = -1;
+    if (big < p0) { big = p0; arg = 0; }
+    if (big < p1) { big = p1; arg = 1; }
+    if (big < p2) { big = p2; arg = 2; }
+    return (uint8_t)arg;
+}
+
+} // namespace famseq

@@ -1,0 +1,397 @@
+// engine.cu -- the C ABI of include/famseq_b200.h: engine life cycle, host-buffer pipeline and the
+// dispatch to the three method kernels.  One engine drives one GPU; multi-GPU runs use one engine
+// (one process, or one host thread) per device with the variants sharded between them.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../../include/famseq_b200.h"
+#include "../host/bn_planner.hpp"
+#include "../host/es_compiler.hpp"
+#include "../host/mcmc_planner.hpp"
+#include "../host/pedigree.hpp"
+#include "kernels.hpp"
+
+using namespace famseq;
+
+static_assert((int)TAB_AUTO == (int)K_TAB_AUTO && (int)TAB_XF == (int)K_TAB_XF && (int)TAB_XM == (int)K_TAB_XM,
+              "host and device table ids differ");
+
+namespace {
+thread_local std::string g_last_error;
+int fail(int code, const std::string &msg) {
+    g_last_error = msg;
+    return code;
+}
+int cuda_fail(cudaError_t rc, const char *what) {
+    return fail(FS_E_CUDA, std::string(what) + ": " + cudaGetErrorString(rc));
+}
+#define FS_CUDA(call)                                                                                        \
+    do {                                                                                                     \
+        cudaError_t rc__ = (call);                                                                           \
+        if (rc__ != cudaSuccess) return cuda_fail(rc__, #call);                                              \
+    } while (0)
+
+constexpr int kPipelineDepth = 3;
+
+struct DeviceChunk {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t k0 = nullptr, k1 = nullptr;
+    double *lk = nullptr, *post = nullptr, *single = nullptr;
+    uint8_t *flags = nullptr, *gt = nullptr, *status = nullptr;
+    int64_t capacity = 0; // variants
+    int64_t in_flight = 0;
+};
+} // namespace
+
+struct fs_engine {
+    Pedigree ped;
+    fs_params params;
+    RunConstants C;
+    int device = -1;
+    size_t smem_limit = 0;
+    int sm_count = 0;
+
+    EsParams es;
+    int es_rc = FS_OK;
+    std::string es_err;
+    int es_tb = 0;
+
+    BnParams bn;
+    int bn_rc = FS_OK;
+    std::string bn_err;
+
+    McmcParams mcmc;
+    int mcmc_rc = FS_OK;
+    std::string mcmc_err;
+    int mcmc_tb = 0;
+
+    DeviceChunk chunk[kPipelineDepth];
+    int64_t launches = 0;
+    double last_kernel_ms = 0;
+};
+
+extern "C" {
+
+void fs_default_params(fs_params *p) {
+    if (!p) return;
+    p->mrate = 1e-7;
+    p->lrc = 1.0;
+    const double n[3] = {0.9985, 0.001, 0.0005}, k[3] = {0.45, 0.1, 0.45};
+    const double xn[3] = {0.999, 0, 0.001}, xk[3] = {0.5, 0, 0.5};
+    std::memcpy(p->geno_prob_n, n, sizeof n);
+    std::memcpy(p->geno_prob_k, k, sizeof k);
+    std::memcpy(p->geno_prob_xn, xn, sizeof xn);
+    std::memcpy(p->geno_prob_xk, xk, sizeof xk);
+}
+
+int fs_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+const char *fs_last_error(void) { return g_last_error.c_str(); }
+
+static void release_chunks(fs_engine *e) {
+    for (DeviceChunk &c : e->chunk) {
+        cudaFree(c.lk);
+        cudaFree(c.post);
+        cudaFree(c.single);
+        cudaFree(c.flags);
+        cudaFree(c.gt);
+        cudaFree(c.status);
+        if (c.k0) cudaEventDestroy(c.k0);
+        if (c.k1) cudaEventDestroy(c.k1);
+        if (c.stream) cudaStreamDestroy(c.stream);
+        c = DeviceChunk();
+    }
+}
+
+void fs_destroy(fs_engine *e) {
+    if (!e) return;
+    if (e->device >= 0) {
+        cudaSetDevice(e->device);
+        release_chunks(e);
+    }
+    delete e;
+}
+
+int fs_create(const fs_pedigree *ped, const fs_params *params, int device, fs_engine **out) {
+    if (!ped || !out) return fail(FS_E_ARG, "fs_create: null argument");
+    *out = nullptr;
+    fs_params prm;
+    if (params)
+        prm = *params;
+    else
+        fs_default_params(&prm);
+    fs_engine *e = new (std::nothrow) fs_engine();
+    if (!e) return fail(FS_E_NOMEM, "out of host memory");
+    std::string err;
+    int rc = build_pedigree(ped->n, ped->id, ped->mother_id, ped->father_id, ped->gender, ped->s, ped->cols,
+                            e->ped, err);
+    if (rc != FS_OK) {
+        delete e;
+        return fail(rc, err);
+    }
+    if (e->ped.n > FS_MAX_MEMBERS) {
+        delete e;
+        return fail(FS_E_TOO_LARGE, "pedigree has more than " + std::to_string(FS_MAX_MEMBERS) + " members");
+    }
+    e->params = prm;
+    e->device = device;
+
+    // ---- per-run constants -----------------------------------------------------------------------
+    RunConstants &C = e->C;
+    std::memset(&C, 0, sizeof C);
+    build_tables(prm.mrate, C.tab);
+    std::memcpy(C.prior[0], prm.geno_prob_n, 24);
+    std::memcpy(C.prior[1], prm.geno_prob_k, 24);
+    std::memcpy(C.prior[2], prm.geno_prob_xn, 24);
+    std::memcpy(C.prior[3], prm.geno_prob_xk, 24);
+    C.lrc = prm.lrc;
+    C.n = e->ped.n;
+    C.s = e->ped.s();
+    for (int c = 0; c < C.s; c++) C.col_male[c] = (uint8_t)e->ped.male[e->ped.cols[c]];
+    // calPostProbSingle fails the variant when ANY member's row sum is <= 0 (family.cpp:1433-1439);
+    // for unsequenced members (lk = 1,1,1) that depends only on the prior vector in use.
+    for (int f = 0; f < 4; f++) {
+        const int known = f & 1, chrx = (f >> 1) & 1;
+        bool bad = false;
+        for (int i = 0; i < e->ped.n; i++) {
+            if (e->ped.col_of[i] >= 0) continue;
+            const double *pr = (chrx && e->ped.male[i]) ? C.prior[known ? 3 : 2] : C.prior[known ? 1 : 0];
+            double r[3];
+            for (int g = 0; g < 3; g++) r[g] = 1.0 * pr[g];
+            double s = 0;
+            for (int g = 0; g < 3; g++) s = s + r[g];
+            if (s <= 0) bad = true;
+        }
+        C.unseq_fail[f] = bad;
+    }
+
+    // ---- pedigree compilers ----------------------------------------------------------------------
+    e->es.C = C;
+    e->es_rc = compile_es_program(e->ped, e->es.prog, e->es_err);
+    e->bn.C = C;
+    e->bn_rc = build_bn_plan(e->ped, e->bn.plan, e->bn_err);
+    e->mcmc.C = C;
+    e->mcmc_rc = build_mcmc_plan(e->ped, e->mcmc.plan, e->mcmc_err);
+
+    if (device >= 0) {
+        cudaError_t crc = cudaSetDevice(device);
+        cudaDeviceProp prop;
+        if (crc == cudaSuccess) crc = cudaGetDeviceProperties(&prop, device);
+        if (crc != cudaSuccess) {
+            delete e;
+            return cuda_fail(crc, "fs_create: no usable CUDA device (there is no CPU fallback)");
+        }
+        if (prop.major < 10) {
+            delete e;
+            return fail(FS_E_CUDA, std::string("fs_create: device ") + prop.name + " is sm_" +
+                                       std::to_string(prop.major * 10 + prop.minor) +
+                                       "; this library carries sm_100a code only");
+        }
+        e->smem_limit = prop.sharedMemPerBlockOptin;
+        e->sm_count = prop.multiProcessorCount;
+        if (e->es_rc == FS_OK) {
+            e->es_tb = es_pick_block(e->es, e->smem_limit);
+            if (e->es_tb == 0) {
+                e->es_rc = FS_E_TOO_LARGE;
+                e->es_err = "pedigree too large for the ES kernel: message scratch exceeds shared memory";
+            }
+        }
+        if (e->bn_rc == FS_OK && bn_smem_bytes(e->bn) > e->smem_limit) {
+            e->bn_rc = FS_E_TOO_LARGE;
+            e->bn_err = "pedigree too large for the BN kernel: per-thread odometer state exceeds shared memory";
+        }
+        if (e->mcmc_rc == FS_OK) {
+            e->mcmc_tb = mcmc_pick_block(e->mcmc, e->smem_limit, prop.sharedMemPerMultiprocessor);
+            if (e->mcmc_tb == 0) {
+                e->mcmc_rc = FS_E_TOO_LARGE;
+                e->mcmc_err = "pedigree too large for the MCMC kernel: chain state exceeds shared memory";
+            }
+        }
+    }
+    *out = e;
+    return FS_OK;
+}
+
+int fs_get_info(const fs_engine *e, fs_info *out) {
+    if (!e || !out) return fail(FS_E_ARG, "fs_get_info: null argument");
+    std::memset(out, 0, sizeof *out);
+    out->n = e->ped.n;
+    out->s = e->ped.s();
+    out->n_founders = e->ped.n_founders();
+    out->has_loop = e->ped.has_loop;
+    out->es_ops = e->es_rc == FS_OK ? e->es.prog.n_ops : 0;
+    out->es_slots = e->es_rc == FS_OK ? e->es.prog.n_slots : 0;
+    out->bn_levels = e->bn_rc == FS_OK ? e->bn.plan.n_levels : 0;
+    out->bn_group = e->bn_rc == FS_OK ? e->bn.plan.group : 0;
+    out->mcmc_links = e->mcmc_rc == FS_OK ? e->mcmc.plan.n_links : 0;
+    out->device = e->device;
+    out->kernel_launches = e->launches;
+    return FS_OK;
+}
+
+int fs_get_tables(const fs_engine *e, double *pcp2, double *pcp2_xf, double *pcp2_xm, int32_t *mother,
+                  int32_t *father) {
+    if (!e) return fail(FS_E_ARG, "fs_get_tables: null engine");
+    if (pcp2) std::memcpy(pcp2, e->C.tab[TAB_AUTO], 27 * 8);
+    if (pcp2_xf) std::memcpy(pcp2_xf, e->C.tab[TAB_XF], 27 * 8);
+    if (pcp2_xm) std::memcpy(pcp2_xm, e->C.tab[TAB_XM], 27 * 8);
+    for (int i = 0; i < e->ped.n; i++) {
+        if (mother) mother[i] = e->ped.mother[i];
+        if (father) father[i] = e->ped.father[i];
+    }
+    return FS_OK;
+}
+
+void *fs_alloc_pinned(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void fs_free_pinned(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+double fs_last_kernel_ms(const fs_engine *e) { return e ? e->last_kernel_ms : 0.0; }
+
+// One kernel launch for `B.V` variants already on the device.
+static int dispatch(fs_engine *e, int method, const BatchPtrs &B, int32_t burn, int32_t rep, uint64_t seed,
+                    int64_t v_offset, cudaStream_t stream) {
+    if (B.V == 0) return FS_OK;
+    switch (method) {
+    case FS_METHOD_ES: {
+        if (e->es_rc != FS_OK) return fail(e->es_rc, e->es_err);
+        FS_CUDA(launch_es(e->es, B, e->es_tb, stream));
+        break;
+    }
+    case FS_METHOD_BN: {
+        if (e->bn_rc != FS_OK) return fail(e->bn_rc, e->bn_err);
+        FS_CUDA(launch_bn(e->bn, B, e->sm_count, stream));
+        break;
+    }
+    case FS_METHOD_MCMC: {
+        if (e->mcmc_rc != FS_OK) return fail(e->mcmc_rc, e->mcmc_err);
+        if (burn < 0 || rep <= 0) return fail(FS_E_ARG, "MCMC needs burn >= 0 and rep >= 1");
+        FS_CUDA(launch_mcmc(e->mcmc, B, e->mcmc_tb, burn, rep, seed, v_offset, stream));
+        break;
+    }
+    default:
+        return fail(FS_E_ARG, "method must be 1 (BN), 2 (ES) or 3 (MCMC)");
+    }
+    e->launches++;
+    return FS_OK;
+}
+
+int fs_run_device(fs_engine *e, int method, int64_t V, const double *d_lk, const uint8_t *d_flags, int32_t burn,
+                  int32_t rep, uint64_t seed, int64_t v_offset, double *d_post, double *d_single,
+                  uint8_t *d_gt, uint8_t *d_status, void *stream) {
+    if (!e) return fail(FS_E_ARG, "fs_run_device: null engine");
+    if (e->device < 0) return fail(FS_E_CUDA, "engine was created without a device (there is no CPU fallback)");
+    if (V < 0 || (V > 0 && (!d_lk || !d_post || !d_single || !d_gt || !d_status)))
+        return fail(FS_E_ARG, "fs_run_device: null buffer");
+    if ((reinterpret_cast<uintptr_t>(d_lk) | reinterpret_cast<uintptr_t>(d_post) |
+         reinterpret_cast<uintptr_t>(d_single)) & 15u)
+        return fail(FS_E_ARG, "fs_run_device: lk/post/single must be 16-byte aligned");
+    FS_CUDA(cudaSetDevice(e->device));
+    BatchPtrs B{d_lk, d_flags, d_post, d_single, d_gt, d_status, V};
+    return dispatch(e, method, B, burn, rep, seed, v_offset, static_cast<cudaStream_t>(stream));
+}
+
+static int ensure_chunks(fs_engine *e, int64_t cap) {
+    const size_t S = (size_t)e->ped.s();
+    for (DeviceChunk &c : e->chunk) {
+        if (c.capacity >= cap) continue;
+        cudaStream_t st = c.stream;
+        cudaEvent_t k0 = c.k0, k1 = c.k1;
+        cudaFree(c.lk);
+        cudaFree(c.post);
+        cudaFree(c.single);
+        cudaFree(c.flags);
+        cudaFree(c.gt);
+        cudaFree(c.status);
+        c = DeviceChunk();
+        c.stream = st;
+        c.k0 = k0;
+        c.k1 = k1;
+        if (!c.stream) FS_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        if (!c.k0) FS_CUDA(cudaEventCreate(&c.k0));
+        if (!c.k1) FS_CUDA(cudaEventCreate(&c.k1));
+        const size_t nd = (size_t)cap * S * 3 * sizeof(double);
+        FS_CUDA(cudaMalloc(&c.lk, nd ? nd : 16));
+        FS_CUDA(cudaMalloc(&c.post, nd ? nd : 16));
+        FS_CUDA(cudaMalloc(&c.single, nd ? nd : 16));
+        FS_CUDA(cudaMalloc(&c.flags, (size_t)cap));
+        FS_CUDA(cudaMalloc(&c.gt, S ? (size_t)cap * S : 16));
+        FS_CUDA(cudaMalloc(&c.status, (size_t)cap));
+        c.capacity = cap;
+    }
+    return FS_OK;
+}
+
+int fs_run(fs_engine *e, int method, int64_t V, const double *lk, const uint8_t *flags, int32_t burn, int32_t rep,
+           uint64_t seed, int64_t v_offset, double *post, double *single, uint8_t *gt, uint8_t *status) {
+    if (!e) return fail(FS_E_ARG, "fs_run: null engine");
+    if (e->device < 0) return fail(FS_E_CUDA, "engine was created without a device (there is no CPU fallback)");
+    if (V < 0 || (V > 0 && (!lk || !post || !single || !gt || !status))) return fail(FS_E_ARG, "fs_run: null buffer");
+    if (V == 0) return FS_OK;
+    FS_CUDA(cudaSetDevice(e->device));
+    const size_t S = (size_t)e->ped.s();
+    // Chunks of ~48 MB of likelihoods (a multiple of 1024 variants keeps every tile 16-byte aligned)
+    // are cycled through kPipelineDepth streams so that the H2D copy of chunk k+1, the kernel of
+    // chunk k and the D2H copy of chunk k-1 overlap.
+    int64_t cap = (int64_t)((48u << 20) / (S ? S * 24 : 24));
+    cap = std::max<int64_t>(1024, std::min<int64_t>(cap, 1 << 22)) & ~(int64_t)1023;
+    cap = std::min<int64_t>(cap, (V + 1023) & ~(int64_t)1023);
+    int rc = ensure_chunks(e, cap);
+    if (rc != FS_OK) return rc;
+
+    e->last_kernel_ms = 0;
+    auto drain = [&](DeviceChunk &c) -> int {
+        if (!c.in_flight) return FS_OK;
+        FS_CUDA(cudaStreamSynchronize(c.stream));
+        float ms = 0;
+        FS_CUDA(cudaEventElapsedTime(&ms, c.k0, c.k1));
+        e->last_kernel_ms += ms;
+        c.in_flight = 0;
+        return FS_OK;
+    };
+    int slot = 0;
+    for (int64_t v0 = 0; v0 < V; v0 += cap, slot = (slot + 1) % kPipelineDepth) {
+        DeviceChunk &c = e->chunk[slot];
+        if ((rc = drain(c)) != FS_OK) return rc;
+        const int64_t nv = std::min<int64_t>(cap, V - v0);
+        const size_t nd = (size_t)nv * S * 3 * sizeof(double);
+        if (nd) FS_CUDA(cudaMemcpyAsync(c.lk, lk + (size_t)v0 * S * 3, nd, cudaMemcpyHostToDevice, c.stream));
+        if (flags) FS_CUDA(cudaMemcpyAsync(c.flags, flags + v0, (size_t)nv, cudaMemcpyHostToDevice, c.stream));
+        BatchPtrs B{c.lk, flags ? c.flags : nullptr, c.post, c.single, c.gt, c.status, nv};
+        FS_CUDA(cudaEventRecord(c.k0, c.stream));
+        rc = dispatch(e, method, B, burn, rep, seed, v_offset + v0, c.stream);
+        if (rc != FS_OK) return rc;
+        FS_CUDA(cudaEventRecord(c.k1, c.stream));
+        if (nd) {
+            FS_CUDA(cudaMemcpyAsync(post + (size_t)v0 * S * 3, c.post, nd, cudaMemcpyDeviceToHost, c.stream));
+            FS_CUDA(cudaMemcpyAsync(single + (size_t)v0 * S * 3, c.single, nd, cudaMemcpyDeviceToHost, c.stream));
+            FS_CUDA(cudaMemcpyAsync(gt + (size_t)v0 * S, c.gt, (size_t)nv * S, cudaMemcpyDeviceToHost, c.stream));
+        }
+        FS_CUDA(cudaMemcpyAsync(status + v0, c.status, (size_t)nv, cudaMemcpyDeviceToHost, c.stream));
+        c.in_flight = nv;
+    }
+    for (DeviceChunk &c : e->chunk)
+        if ((rc = drain(c)) != FS_OK) return rc;
+    return FS_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,85 @@
+// bn_plan.cpp -- see bn_plan.hpp.
+#include <cstring>
+
+#include "../../../include/famseq_b200.h"
+#include "bn_planner.hpp"
+
+namespace famseq {
+
+int build_bn_plan(const Pedigree &ped, BnPlan &out, std::string &err) {
+    BnPlan p{};
+    const int N = ped.n;
+    if (N > BN_MAX_LEVELS) {
+        err = "The Bayesian-network method enumerates 3^N genotype configurations; N = " + std::to_string(N) +
+              " exceeds the kernel limit of " + std::to_string(BN_MAX_LEVELS) + " members.";
+        return FS_E_TOO_LARGE;
+    }
+    p.n_levels = N;
+
+    // Enumeration order: parents before children; members who have children first (generation by
+    // generation), childless members innermost.  Childless members' factors then depend only on
+    // digits that are fixed outside the innermost loops.
+    std::vector<int> order;
+    std::vector<char> placed(N, 0);
+    for (int pass = 0; pass < 2; pass++) {
+        bool progress = true;
+        while (progress) {
+            progress = false;
+            for (int i = 0; i < N; i++) {
+                if (placed[i]) continue;
+                const bool leaf = ped.children[i].empty();
+                if ((pass == 0) == leaf) continue;
+                if (!ped.founder(i) && (!placed[ped.mother[i]] || !placed[ped.father[i]])) continue;
+                placed[i] = 1;
+                order.push_back(i);
+                progress = true;
+            }
+        }
+    }
+    if ((int)order.size() != N) { // cannot happen: a pedigree is a DAG
+        err = "internal error: pedigree is not a DAG";
+        return FS_E_ARG;
+    }
+    std::vector<int> level_of(N);
+    for (int L = 0; L < N; L++) level_of[order[L]] = L;
+
+    p.u = N < 3 ? N : (N >= 9 ? BN_MAX_UNROLL : 3);
+    p.h = N - p.u < 5 ? N - p.u : 5;
+    p.r = N - p.u - p.h;
+    p.group = 1;
+    for (int k = 0; k < p.h; k++) p.group *= 3;
+    p.vpb = 256 / p.group;
+    if (p.vpb < 1) p.vpb = 1;
+    p.threads = ((p.vpb * p.group + 31) / 32) * 32;
+
+    int off = 0;
+    for (int L = 0; L < N; L++) {
+        const int i = order[L];
+        p.member[L] = (int16_t)i;
+        p.col[L] = (int16_t)ped.col_of[i];
+        p.male[L] = (uint8_t)ped.male[i];
+        p.founder[L] = ped.founder(i);
+        p.sh_m[L] = p.sh_f[L] = BN_ZERO_SHIFT;
+        if (!ped.founder(i)) {
+            p.sh_m[L] = (uint8_t)(2 * level_of[ped.mother[i]]);
+            p.sh_f[L] = (uint8_t)(2 * level_of[ped.father[i]]);
+        }
+        p.tab_off[L] = off;
+        off += ped.founder(i) ? 4 : 36;
+    }
+    p.table_doubles = off;
+    const int first_unrolled = N - p.u;
+    for (int x = 0; x < p.u; x++) {
+        const int i = order[first_unrolled + x];
+        if (ped.founder(i)) continue;
+        for (int y = 0; y < x; y++) {
+            const int j = order[first_unrolled + y];
+            if (ped.mother[i] == j) p.ustride[x][y] = 12; // row = 3*mother + father, 4 doubles per row
+            if (ped.father[i] == j) p.ustride[x][y] = 4;
+        }
+    }
+    out = p;
+    return FS_OK;
+}
+
+} // namespace famseq

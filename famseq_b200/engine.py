@@ -1,0 +1,221 @@
+"""ctypes binding of libfamseq_b200.so (C ABI: include/famseq_b200.h).
+
+This is host-side plumbing for tests and bench.py; the product is the shared library and the
+`FamSeq` command line built from famseq_b200/csrc.  There is no Python or CPU implementation of the
+posterior engine here: if the library is missing the import of this module fails, and if no sm_100
+GPU is usable `Engine(...)` raises.
+
+Names follow the reference's `class family` (src/family.h:262-389): `calPostProbBN`,
+`calPostProbPeeling`, `calPostProbMCMC`, but each call takes a whole batch of variants.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfamseq_b200.so")
+
+BN, ES, MCMC = 1, 2, 3
+FLAG_KNOWN, FLAG_CHRX = 1, 2
+
+FS_ERRORS = {
+    -1: "FS_E_ARG", -2: "FS_E_HALF_PARENTS", -3: "FS_E_GENDER", -4: "FS_E_LOOP", -5: "FS_E_TOO_LARGE",
+    -6: "FS_E_CUDA", -7: "FS_E_NOMEM",
+}
+
+
+class FamSeqError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"{FS_ERRORS.get(code, code)}: {message}")
+        self.code = code
+
+
+class _Pedigree(ctypes.Structure):
+    _fields_ = [("n", ctypes.c_int32), ("id", ctypes.c_void_p), ("mother_id", ctypes.c_void_p),
+                ("father_id", ctypes.c_void_p), ("gender", ctypes.c_void_p), ("s", ctypes.c_int32),
+                ("cols", ctypes.c_void_p)]
+
+
+class Params(ctypes.Structure):
+    """fs_params: -mRate, -LRC and the four prior vectors (reference defaults via `Params.default()`)."""
+    _fields_ = [("mrate", ctypes.c_double), ("lrc", ctypes.c_double), ("geno_prob_n", ctypes.c_double * 3),
+                ("geno_prob_k", ctypes.c_double * 3), ("geno_prob_xn", ctypes.c_double * 3),
+                ("geno_prob_xk", ctypes.c_double * 3)]
+
+    @staticmethod
+    def default() -> "Params":
+        p = Params()
+        lib().fs_default_params(ctypes.byref(p))
+        return p
+
+    def priors(self) -> np.ndarray:
+        return np.array([list(self.geno_prob_n), list(self.geno_prob_k), list(self.geno_prob_xn),
+                         list(self.geno_prob_xk)], dtype=np.float64)
+
+
+class _Info(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_int32) for k in ("n", "s", "n_founders", "has_loop", "es_ops", "es_slots", "bn_levels",
+                                               "bn_group", "mcmc_links", "device")] + [("kernel_launches", ctypes.c_int64)]
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Loads the shared library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(make -C famseq_b200/csrc). There is no CPU or PyTorch fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        P, I32, I64, U64, D = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64, ctypes.c_double
+        L.fs_default_params.restype = None
+        L.fs_default_params.argtypes = [P]
+        L.fs_device_count.restype = ctypes.c_int
+        L.fs_create.restype = ctypes.c_int
+        L.fs_create.argtypes = [P, P, ctypes.c_int, P]
+        L.fs_destroy.restype = None
+        L.fs_destroy.argtypes = [P]
+        L.fs_last_error.restype = ctypes.c_char_p
+        L.fs_run.restype = ctypes.c_int
+        L.fs_run.argtypes = [P, ctypes.c_int, I64, P, P, I32, I32, U64, I64, P, P, P, P]
+        L.fs_run_device.restype = ctypes.c_int
+        L.fs_run_device.argtypes = [P, ctypes.c_int, I64, P, P, I32, I32, U64, I64, P, P, P, P, P]
+        L.fs_get_info.restype = ctypes.c_int
+        L.fs_get_info.argtypes = [P, P]
+        L.fs_get_tables.restype = ctypes.c_int
+        L.fs_get_tables.argtypes = [P, P, P, P, P, P]
+        L.fs_alloc_pinned.restype = P
+        L.fs_alloc_pinned.argtypes = [ctypes.c_size_t]
+        L.fs_free_pinned.restype = None
+        L.fs_free_pinned.argtypes = [P]
+        L.fs_last_kernel_ms.restype = D
+        L.fs_last_kernel_ms.argtypes = [P]
+        _lib = L
+    return _lib
+
+
+EXPORTED_SYMBOLS = ["fs_default_params", "fs_device_count", "fs_create", "fs_destroy", "fs_last_error", "fs_run",
+                    "fs_run_device", "fs_get_info", "fs_get_tables", "fs_alloc_pinned", "fs_free_pinned",
+                    "fs_last_kernel_ms"]
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise FamSeqError(rc, lib().fs_last_error().decode("utf-8", "replace"))
+
+
+def _i32(x):
+    return np.ascontiguousarray(x, dtype=np.int32)
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(ctypes.c_void_p)
+    return ctypes.c_void_p(int(a))  # raw address (e.g. torch.Tensor.data_ptr())
+
+
+@dataclass
+class Result:
+    post: np.ndarray    # [V][S][3] pedigree-aware posterior (FPP)
+    single: np.ndarray  # [V][S][3] individual-only posterior (GPP)
+    gt: np.ndarray      # [V][S] uint8 called genotype (FGT): 0 RR, 1 RA, 2 AA, 255 = the reference's -1
+    status: np.ndarray  # [V] uint8, 1 = "this variant hasn't been calculated" (the reference returned false)
+
+
+class Engine:
+    """One pedigree compiled for one GPU (fs_create / fs_destroy)."""
+
+    def __init__(self, ids, mother_ids, father_ids, genders, cols, params: Params | None = None, device: int = 0):
+        self._h = ctypes.c_void_p()
+        self._keep = [_i32(ids), _i32(mother_ids), _i32(father_ids), _i32(genders), _i32(cols)]
+        ped = _Pedigree(len(self._keep[0]), _ptr(self._keep[0]), _ptr(self._keep[1]), _ptr(self._keep[2]),
+                        _ptr(self._keep[3]), len(self._keep[4]), _ptr(self._keep[4]))
+        self.params = params if params is not None else Params.default()
+        self.device = device
+        _check(lib().fs_create(ctypes.byref(ped), ctypes.byref(self.params), device, ctypes.byref(self._h)))
+        self.n, self.s = ped.n, ped.s
+
+    def close(self) -> None:
+        if self._h:
+            lib().fs_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- introspection ------------------------------------------------------------------------------
+    def info(self) -> dict:
+        i = _Info()
+        _check(lib().fs_get_info(self._h, ctypes.byref(i)))
+        return {k: getattr(i, k) for k, _ in _Info._fields_}
+
+    def tables(self):
+        a, xf, xm = np.zeros(27), np.zeros(27), np.zeros(27)
+        mo, fa = np.zeros(self.n, np.int32), np.zeros(self.n, np.int32)
+        _check(lib().fs_get_tables(self._h, _ptr(a), _ptr(xf), _ptr(xm), _ptr(mo), _ptr(fa)))
+        return a, xf, xm, mo, fa
+
+    def last_kernel_ms(self) -> float:
+        return float(lib().fs_last_kernel_ms(self._h))
+
+    # -- batch calls on host buffers ------------------------------------------------------------------
+    def run(self, method: int, lk, flags=None, burn: int = 1000, rep: int = 100000, seed: int = 0,
+            v_offset: int = 0, out: Result | None = None) -> Result:
+        lk = np.ascontiguousarray(lk, dtype=np.float64)
+        if lk.ndim != 3 or lk.shape[1] != self.s or lk.shape[2] != 3:
+            raise ValueError(f"lk must be [V][{self.s}][3]")
+        V = lk.shape[0]
+        if flags is not None:
+            flags = np.ascontiguousarray(flags, dtype=np.uint8)
+            if flags.shape != (V,):
+                raise ValueError("flags must be [V]")
+        if out is None:
+            out = Result(np.empty((V, self.s, 3)), np.empty((V, self.s, 3)), np.empty((V, self.s), np.uint8),
+                         np.empty(V, np.uint8))
+        _check(lib().fs_run(self._h, method, V, _ptr(lk), _ptr(flags), burn, rep, seed, v_offset, _ptr(out.post),
+                            _ptr(out.single), _ptr(out.gt), _ptr(out.status)))
+        return out
+
+    def run_raw(self, method: int, V: int, lk_ptr, flags_ptr, post_ptr, single_ptr, gt_ptr, status_ptr, burn=1000,
+                rep=100000, seed=0, v_offset=0) -> None:
+        """fs_run on raw HOST addresses (e.g. pinned torch tensors)."""
+        _check(lib().fs_run(self._h, method, V, _ptr(lk_ptr), _ptr(flags_ptr), burn, rep, seed, v_offset, _ptr(post_ptr),
+                            _ptr(single_ptr), _ptr(gt_ptr), _ptr(status_ptr)))
+
+    def run_device(self, method: int, V: int, lk_ptr, flags_ptr, post_ptr, single_ptr, gt_ptr, status_ptr, burn=1000,
+                   rep=100000, seed=0, v_offset=0, stream=0) -> None:
+        """fs_run_device on raw DEVICE addresses; asynchronous on `stream` (a cudaStream_t handle)."""
+        _check(lib().fs_run_device(self._h, method, V, _ptr(lk_ptr), _ptr(flags_ptr), burn, rep, seed, v_offset,
+                                   _ptr(post_ptr), _ptr(single_ptr), _ptr(gt_ptr), _ptr(status_ptr),
+                                   ctypes.c_void_p(int(stream))))
+
+    # -- the reference's method names -------------------------------------------------------------------
+    def calPostProbBN(self, lk, flags=None) -> Result:
+        return self.run(BN, lk, flags)
+
+    def calPostProbPeeling(self, lk, flags=None) -> Result:
+        return self.run(ES, lk, flags)
+
+    def calPostProbMCMC(self, lk, numBurnIn: int, numRep: int, flags=None, seed: int = 0, v_offset: int = 0) -> Result:
+        return self.run(MCMC, lk, flags, burn=numBurnIn, rep=numRep, seed=seed, v_offset=v_offset)
+
+
+def device_count() -> int:
+    return int(lib().fs_device_count())

@@ -1,0 +1,144 @@
+/* famseq_b200.h -- C ABI of the B200-native FamSeq posterior-genotype engine.
+ *
+ * This is the drop-in boundary for the reference's in-process seam `class family`
+ * (/root/reference/src/family.h:62-390).  The reference is called once per variant from its
+ * two record loops (src/file.cpp:595-682 / :833-920 for VCF, :1743-1806 for likelihood files);
+ * this ABI is the batched equivalent: one call computes a whole block of variants on one GPU.
+ *
+ *   reference (per variant)                               this ABI (per batch)
+ *   ----------------------------------------------------  -----------------------------------
+ *   family(mem, mRate)            family.cpp:78-126       fs_create(ped, params, device, &eng)
+ *   set_genoProb{N,K,XN,XK}       family.cpp:552-574        (fs_params.geno_prob_*)
+ *   set_lc                        family.cpp:253-257        (fs_params.lrc)
+ *   init / setRelation / checkPed family.cpp:221-238        (inside fs_create; same error rules)
+ *   set_mapV2P / set_mapP2V       family.cpp:357-376        (fs_pedigree.cols)
+ *   set_LK(N x 3)                 family.cpp:698-748      lk[V][S][3]   (sequenced columns only;
+ *                                                           unsequenced members are (1,1,1))
+ *   calPostProbBN(Known,chrType)  family.cpp:750-1124     fs_run(..., FS_METHOD_BN, ...)
+ *   calPostProbPeeling(...)       family.cpp:1126-1403    fs_run(..., FS_METHOD_ES, ...)
+ *   calPostProbMCMC(burn,rep,...) family.cpp:1932-2096    fs_run(..., FS_METHOD_MCMC, ...)
+ *   bool return value             file.cpp:607-619        status[v] (1 = "hasn't been calculated")
+ *   get_postProb(true)            family.cpp:576-604      post[V][S][3]
+ *   get_postProbSingle(true)      family.cpp:606-634      single[V][S][3]
+ *   get_postRlt()                 family.cpp:636-665      gt[V][S]  (0,1,2; 255 = the reference's -1)
+ *
+ * All entry points are plain C: pointers and sizes only.  Every function returns FS_OK (0) or a
+ * negative FS_E_* code; fs_last_error() returns a thread-local message for the last failure.
+ * There is no CPU fallback: without a usable sm_100 device fs_create fails with FS_E_CUDA.
+ */
+#ifndef FAMSEQ_B200_H_
+#define FAMSEQ_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FS_ABI_VERSION 1
+
+enum fs_method { FS_METHOD_BN = 1, FS_METHOD_ES = 2, FS_METHOD_MCMC = 3 }; /* the CLI's -method 1|2|3 */
+
+enum fs_flag { FS_FLAG_KNOWN = 1, /* VCF ID != "."  (file.cpp:476-480) */
+               FS_FLAG_CHRX = 2 /* CHROM in {X,chrX,CHRX} (file.cpp:482-486) */ };
+
+enum fs_error {
+    FS_OK = 0,
+    FS_E_ARG = -1,          /* bad argument */
+    FS_E_HALF_PARENTS = -2, /* exactly one parent known: "This is not a fulfill family" (family.cpp:318-322) */
+    FS_E_GENDER = -3,       /* mother not female / father not male (family.cpp:204-219) */
+    FS_E_LOOP = -4,         /* ES asked on a pedigree with a marriage/consanguinity loop (the reference crashes) */
+    FS_E_TOO_LARGE = -5,    /* pedigree exceeds a kernel limit (message says which) */
+    FS_E_CUDA = -6,         /* CUDA runtime failure or no sm_100 device */
+    FS_E_NOMEM = -7
+};
+
+/* The ped rows (file.cpp:24-62) plus the input-column mapping built by the drivers
+ * (file.cpp:204-223, :1673-1689). */
+typedef struct fs_pedigree {
+    int32_t n;                /* pedigree members (rows of the ped file)                              */
+    const int32_t *id;        /* [n] individual id                                                    */
+    const int32_t *mother_id; /* [n] mother's id, any id not present among `id` means "founder"       */
+    const int32_t *father_id; /* [n]                                                                  */
+    const int32_t *gender;    /* [n] 1 male, 2 female (anything else is treated as "not male")        */
+    int32_t s;                /* sequenced input columns that matched a ped row                       */
+    const int32_t *cols;      /* [s] ped row of each matched input column, in input-column order      */
+} fs_pedigree;
+
+typedef struct fs_params {
+    double mrate;           /* -mRate,     default 1e-7 (checkInput.cpp:157)           */
+    double lrc;             /* -LRC,       default 1    (checkInput.cpp:167)           */
+    double geno_prob_n[3];  /* -genoProbN, default 0.9985 0.001 0.0005 (family.cpp:97) */
+    double geno_prob_k[3];  /* -genoProbK, default 0.45 0.1 0.45                       */
+    double geno_prob_xn[3]; /* -genoProbXN a b -> (a,0,b), default 0.999 0 0.001       */
+    double geno_prob_xk[3]; /* -genoProbXK a b -> (a,0,b), default 0.5 0 0.5           */
+} fs_params;
+
+typedef struct fs_engine fs_engine;
+
+/* Fills *p with the reference defaults. */
+void fs_default_params(fs_params *p);
+
+/* Number of CUDA devices visible to the library (0 when there is none / no driver). */
+int fs_device_count(void);
+
+/* Builds the pedigree program (topology, transmission tables, ES message schedule, BN enumeration
+ * plan, Gibbs neighbour lists) on the host and uploads it to `device`.  `device` < 0 builds the host
+ * side only (no CUDA call is made; fs_run* then fail with FS_E_CUDA) -- used by CPU-only tests of the
+ * pedigree compiler and by `FamSeq --check-ped`. */
+int fs_create(const fs_pedigree *ped, const fs_params *params, int device, fs_engine **out);
+void fs_destroy(fs_engine *e);
+
+/* Thread-local text of the last error raised on the calling thread. */
+const char *fs_last_error(void);
+
+/* Blocking batch call on HOST buffers (pinned memory recommended; see fs_alloc_pinned).
+ *   lk      [V][S][3] FP64 raw likelihoods Pr(D|G), input-column order
+ *   flags   [V]       FS_FLAG_* bits (NULL = all zero, as the LK driver does, file.cpp:1751)
+ *   burn, rep         Gibbs burn-in / sampling sweeps (ignored for BN, ES)
+ *   seed, v_offset    Philox key and global index of variant 0: variant v draws from the stream
+ *                     keyed (seed, v_offset + v), so any sharding of the input gives identical bytes
+ *   post, single [V][S][3], gt [V][S], status [V]   outputs (see the table above)
+ * The call is internally pipelined (H2D / kernel / D2H on separate streams). */
+int fs_run(fs_engine *e, int method, int64_t V, const double *lk, const uint8_t *flags, int32_t burn,
+           int32_t rep, uint64_t seed, int64_t v_offset, double *post, double *single, uint8_t *gt,
+           uint8_t *status);
+
+/* Same computation on DEVICE buffers, enqueued on `stream` (a cudaStream_t, NULL = default stream) and
+ * not synchronised: this is the kernel-only path that bench.py times with CUDA events. */
+int fs_run_device(fs_engine *e, int method, int64_t V, const double *d_lk, const uint8_t *d_flags, int32_t burn,
+                  int32_t rep, uint64_t seed, int64_t v_offset, double *d_post, double *d_single,
+                  uint8_t *d_gt, uint8_t *d_status, void *stream);
+
+/* Introspection of the compiled pedigree program (all fields are counts). */
+typedef struct fs_info {
+    int32_t n, s;             /* members, sequenced columns                                          */
+    int32_t n_founders;       /*                                                                      */
+    int32_t has_loop;         /* 1 when the marriage graph has a cycle (ES unavailable)               */
+    int32_t es_ops;           /* message-program length                                               */
+    int32_t es_slots;         /* FP64 3-vectors of per-variant scratch the ES program needs           */
+    int32_t bn_levels;        /* enumeration depth (= n)                                              */
+    int32_t bn_group;         /* threads cooperating on one variant in the BN kernel                  */
+    int32_t mcmc_links;       /* parent-child links visited per Gibbs sweep                           */
+    int32_t device;           /* CUDA device or -1                                                    */
+    int64_t kernel_launches;  /* kernels launched by this engine so far                               */
+} fs_info;
+int fs_get_info(const fs_engine *e, fs_info *out);
+
+/* Copies the 3 x 27 transmission tables [g][mother][father] (autosome, X daughter, X son) and the
+ * parent rows (-1 = founder) the engine built; any pointer may be NULL. */
+int fs_get_tables(const fs_engine *e, double *pcp2, double *pcp2_xf, double *pcp2_xm, int32_t *mother,
+                  int32_t *father);
+
+/* Pinned host memory helpers for callers without their own CUDA runtime binding. */
+void *fs_alloc_pinned(size_t bytes);
+void fs_free_pinned(void *p);
+
+/* Milliseconds the kernels of the last fs_run on this engine spent on the device (CUDA events). */
+double fs_last_kernel_ms(const fs_engine *e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FAMSEQ_B200_H_ */

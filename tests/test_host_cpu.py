@@ -1,0 +1,121 @@
+"""CPU-only checks of the product's host side: the C-ABI library loads and exports every symbol the header
+declares, and the pedigree compilers (fs_create with device = -1: no CUDA call) agree with the oracle's view of
+the same pedigree.  No compute call is made here (there is no CPU compute path)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import famseq_b200 as fs
+from famseq_b200 import synth
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "famseq_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(fs_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = fs.lib()
+    syms = header_symbols()
+    assert len(syms) >= 12
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in include/famseq_b200.h but not exported"
+    assert sorted(fs.engine.EXPORTED_SYMBOLS) == syms
+
+
+def host_engine(ped, params=None):
+    return fs.Engine(ped.ids, ped.mids, ped.fids, ped.genders, ped.sequenced_cols(), params=params, device=-1)
+
+
+@pytest.mark.parametrize("mrate", [1e-7, 0.0, 1e-4, 0.01, 0.5])
+def test_transmission_tables_bit_identical_to_oracle(mrate):
+    prm = fs.Params.default()
+    prm.mrate = mrate
+    with host_engine(synth.trio(), prm) as e:
+        a, xf, xm, _, _ = e.tables()
+    oa, oxf, oxm = O.tables(mrate)
+    assert np.array_equal(a, oa) and np.array_equal(xf, oxf) and np.array_equal(xm, oxm)
+
+
+@pytest.mark.parametrize("name", sorted(synth.PEDIGREES))
+def test_topology_matches_oracle(name):
+    ped = synth.PEDIGREES[name]()
+    with host_engine(ped) as e:
+        _, _, _, mo, fa = e.tables()
+        info = e.info()
+    n = ped.n
+    i32 = lambda x: np.ascontiguousarray(x, dtype=np.int32)
+    omo, ofa = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    ids, mids, fids, gen = i32(ped.ids), i32(ped.mids), i32(ped.fids), i32(ped.genders)
+    assert O.lib().fso_topology(n, p(ids), p(mids), p(fids), p(gen), p(omo), p(ofa)) == 0
+    assert np.array_equal(mo, omo) and np.array_equal(fa, ofa)
+    assert info["n"] == n and info["s"] == n
+    assert info["n_founders"] == int((omo < 0).sum())
+    assert info["mcmc_links"] == 2 * int((omo >= 0).sum())
+    assert info["bn_levels"] == (n if n <= 31 else 0)
+
+
+def test_loop_detection_and_es_refusal():
+    for name, loop in (("trio", 0), ("ped14", 0), ("half_sibs", 0), ("three_wives", 0), ("cousins_loop", 1), ("ped40", 1)):
+        with host_engine(synth.PEDIGREES[name]()) as e:
+            info = e.info()
+            assert info["has_loop"] == loop, name
+            assert (info["es_ops"] == 0) == bool(loop), name
+
+
+def test_es_program_sizes():
+    with host_engine(synth.trio()) as e:
+        i = e.info()
+        # trio: pos(father->mother), pos(mother->father), ant(child) and one FIN per member; products ant*lk of the
+        # two founders are shared
+        assert i["es_ops"] == 8 and i["es_slots"] <= 5
+    with host_engine(synth.ped14()) as e:
+        i = e.info()
+        assert 14 <= i["es_ops"] < 80 and i["es_slots"] < 40
+
+
+def test_pedigree_errors_follow_the_reference():
+    # one parent only: "This is not a fulfill family" (family.cpp:318-322)
+    with pytest.raises(fs.FamSeqError) as ei:
+        fs.Engine([1, 2, 3], [0, 0, 2], [0, 0, 0], [1, 2, 1], [0, 1, 2], device=-1)
+    assert ei.value.code == -2 and "fulfill" in str(ei.value)
+    # mother is male (family.cpp:204-219)
+    with pytest.raises(fs.FamSeqError) as ei:
+        fs.Engine([1, 2, 3], [0, 0, 1], [0, 0, 2], [1, 2, 1], [0, 1, 2], device=-1)
+    assert ei.value.code == -3
+    # BN size limit
+    n = 40
+    with host_engine(synth.ped40()) as e:
+        assert e.info()["bn_levels"] == 0  # 3^40 configurations: refused, not attempted
+
+
+def test_no_cpu_fallback():
+    with host_engine(synth.trio()) as e:
+        lk = np.ones((4, 3, 3))
+        with pytest.raises(fs.FamSeqError) as ei:
+            e.run(fs.ES, lk)
+        assert ei.value.code == -6 and "no CPU fallback" in str(ei.value)
+
+
+def test_product_does_not_import_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "famseq_b200")):
+        for f in files:
+            if f.endswith((".py", ".cpp", ".hpp", ".cu", ".cuh", ".h")) or f == "Makefile":
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle" not in text.lower(), f"{os.path.join(dirpath, f)} mentions the oracle"
+
+
+def test_synthetic_generator_is_sliceable():
+    ped = synth.ped14()
+    full, ff = synth.synth_likelihoods(ped, 70000, seed=3, x_fraction=0.1)
+    part, pf = synth.synth_likelihoods(ped, 1000, seed=3, v0=65000, x_fraction=0.1)
+    assert np.array_equal(full[65000:66000], part) and np.array_equal(ff[65000:66000], pf)
+    assert full.min() > 0 and full.max() == 1.0

@@ -1,0 +1,55 @@
+"""Shared helpers for the parity tests."""
+from __future__ import annotations
+
+import glob
+import os
+
+import numpy as np
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+REL_TOL = 1e-9  # north_star: BN and ES posteriors within 1e-9 relative of the reference CPU path
+
+
+def golden_cases(pattern="*"):
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, pattern + ".npz")))
+
+
+def load_case(name):
+    return dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+
+
+class CasePed:
+    """Duck-typed pedigree (same attribute names as oracle.Pedigree / synth.PedFile)."""
+
+    def __init__(self, c):
+        self.ids, self.mids, self.fids, self.genders = (c[k].tolist() for k in ("ids", "mids", "fids", "genders"))
+        self.names = ["x"] * len(self.ids)
+        self.n = len(self.ids)
+
+
+def rel_err(a, b):
+    """max |a-b| / |b| with exact zeros required to match exactly."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    zero_mismatch = (a == 0) != (b == 0)
+    if zero_mismatch.any():
+        return np.inf
+    nz = b != 0
+    if not nz.any():
+        return 0.0
+    return float(np.max(np.abs(a[nz] - b[nz]) / np.abs(b[nz])))
+
+
+def assert_parity(got, want, tol=REL_TOL, what=""):
+    """got: object with post/single/gt/status; want: dict with the same keys (reference or oracle)."""
+    ws = np.asarray(want["status"]).astype(np.uint8)
+    gs = np.asarray(got.status).astype(np.uint8)
+    assert np.array_equal(gs, ws), f"{what}: status differs at {np.nonzero(gs != ws)[0][:10]}"
+    ok = ws == 0
+    wgt = np.asarray(want["gt"]).astype(np.int64) & 0xff
+    ggt = np.asarray(got.gt).astype(np.int64) & 0xff
+    assert np.array_equal(ggt[ok], wgt[ok]), f"{what}: called genotypes differ ({int((ggt[ok] != wgt[ok]).sum())} entries)"
+    e1 = rel_err(np.asarray(got.single)[ok], np.asarray(want["single"])[ok])
+    e2 = rel_err(np.asarray(got.post)[ok], np.asarray(want["post"])[ok])
+    assert e1 <= tol, f"{what}: single posterior rel err {e1:.3e} > {tol}"
+    assert e2 <= tol, f"{what}: pedigree posterior rel err {e2:.3e} > {tol}"
+    return e1, e2
