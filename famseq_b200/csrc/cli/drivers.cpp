@@ -1,0 +1,717 @@
+// drivers.cpp -- see drivers.hpp.
+//
+// The reference handles one record at a time (parse, set_LK, calPostProb*, print).  Here the text side
+// keeps the reference's record rules and output bytes, but records are collected into batches of up to
+// kBatch variants, sent through one fs_run() call (H2D / kernel / D2H pipelined inside the engine) and
+// then printed in input order.  Likelihood decoding (pow, exp) and Phred encoding (log10) stay on the
+// host with libm so that the engine sees bit-identical inputs ("hard parts").
+#include "drivers.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <limits>
+#include <sstream>
+#include <string_view>
+
+#include "../../../include/famseq_b200.h"
+
+namespace famseq_cli {
+
+RunStats g_stats;
+bool g_engine_failed = false;
+
+namespace {
+
+using sv = std::string_view;
+constexpr size_t kBatch = 1u << 18;
+
+double now() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// The reference's split() (normal.cpp:15-53): single-character delimiter, empty fields are kept, a trailing
+// delimiter yields a trailing empty field, an empty source yields nothing.
+void split(sv src, char tok, std::vector<sv> &out) {
+    out.clear();
+    if (src.empty()) return;
+    size_t head = 0;
+    for (;;) {
+        const size_t tail = src.find(tok, head);
+        if (tail == sv::npos) break;
+        out.push_back(src.substr(head, tail - head));
+        head = tail + 1;
+    }
+    out.push_back(src.substr(head));
+}
+
+double to_double(sv s) { // atof
+    char buf[64];
+    const size_t n = std::min(s.size(), sizeof buf - 1);
+    std::memcpy(buf, s.data(), n);
+    buf[n] = 0;
+    return std::strtod(buf, nullptr);
+}
+
+int to_int(sv s) { // atoi
+    char buf[32];
+    const size_t n = std::min(s.size(), sizeof buf - 1);
+    std::memcpy(buf, s.data(), n);
+    buf[n] = 0;
+    return std::atoi(buf);
+}
+
+bool read_file(const std::string &path, std::string &data) {
+    FILE *f = std::fopen(path.c_str(), "rb");
+    if (!f) return false;
+    std::fseek(f, 0, SEEK_END);
+    const long sz = std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    data.resize(sz > 0 ? (size_t)sz : 0);
+    const size_t got = data.empty() ? 0 : std::fread(&data[0], 1, data.size(), f);
+    std::fclose(f);
+    data.resize(got);
+    return true;
+}
+
+// getline()-style cursor over an in-memory file.  Mirrors `while(!fin.eof()) getline(fin, line)`: after the last
+// newline one more, empty, line is delivered.
+struct Lines {
+    const std::string &data;
+    size_t pos = 0;
+    bool done = false;
+    explicit Lines(const std::string &d) : data(d) {}
+    bool next(sv &line) {
+        if (done) return false;
+        const size_t nl = data.find('\n', pos);
+        if (nl == std::string::npos) {
+            line = sv(data).substr(pos);
+            done = true;
+        } else {
+            line = sv(data).substr(pos, nl - pos);
+            pos = nl + 1;
+        }
+        return true;
+    }
+};
+
+// ostream's default formatting of a double is printf's %g with 6 significant digits.
+void put_number(std::string &out, double v) {
+    char buf[40];
+    const int n = std::snprintf(buf, sizeof buf, "%g", v);
+    out.append(buf, (size_t)n);
+}
+
+// file.cpp:702-749: -10*log10(p); +inf is printed as 99999, everything else as its absolute value
+void put_phred(std::string &out, double p) {
+    const double v = -10 * std::log10(p);
+    if (v == std::numeric_limits<double>::infinity())
+        out += "99999";
+    else
+        put_number(out, std::fabs(v));
+}
+
+void put_calls(std::string &out, const double *single, const double *post, uint8_t gt) {
+    put_phred(out, single[0]); out += ',';
+    put_phred(out, single[1]); out += ',';
+    put_phred(out, single[2]); out += ':';
+    put_phred(out, post[0]); out += ',';
+    put_phred(out, post[1]); out += ',';
+    put_phred(out, post[2]); out += ':';
+    out += gt == 0 ? "0/0\t" : (gt == 1 ? "0/1\t" : "1/1\t"); // file.cpp:750-761: anything but 0 and 1 prints 1/1
+}
+
+const char *kFormatLines =
+    "##FORMAT=<ID=FPP,Number=G,Type=Integer,Description=\"Normalized, Phred-scaled for posterior probability calculated by FamSeqPro\">\n"
+    "##FORMAT=<ID=FGT,Number=1,Type=String,Description=\"Genotype called by FamSeqPro\">\n";
+
+struct Priors {
+    double n[3], k[3], xn[3], xk[3];
+};
+
+void fill_params(const CommonOptions &o, fs_params &p, Priors &shown) {
+    fs_default_params(&p);
+    p.mrate = o.mrate;
+    p.lrc = o.lrc;
+    auto set = [](const std::vector<double> &src, double *dst) {
+        if (src.size() == 3) std::copy(src.begin(), src.end(), dst);
+    };
+    set(o.geno_prob_n, p.geno_prob_n);
+    set(o.geno_prob_k, p.geno_prob_k);
+    set(o.geno_prob_xn, p.geno_prob_xn);
+    set(o.geno_prob_xk, p.geno_prob_xk);
+    std::memcpy(shown.n, p.geno_prob_n, 24);
+    std::memcpy(shown.k, p.geno_prob_k, 24);
+    std::memcpy(shown.xn, p.geno_prob_xn, 24);
+    std::memcpy(shown.xk, p.geno_prob_xk, 24);
+}
+
+void put_triplet(std::string &out, const double *v) {
+    put_number(out, v[0]); out += ':';
+    put_number(out, v[1]); out += ':';
+    put_number(out, v[2]);
+}
+
+// Maps input columns to ped rows by exact name match, first matching ped row wins (file.cpp:209-220).
+struct ColumnMap {
+    std::vector<int> ped_row;  // per input column: ped row or -1
+    std::vector<int> matched;  // input columns with a ped row, in input order
+    std::vector<int> unique;   // per matched column: index into `engine_cols`
+    std::vector<int32_t> engine_cols; // distinct ped rows, order of first appearance
+    int real_num_ind() const { return (int)matched.size(); }
+};
+
+ColumnMap map_columns(const std::vector<sv> &names, size_t first, const PedRows &ped) {
+    ColumnMap m;
+    for (size_t c = first; c < names.size(); c++) {
+        int row = -1;
+        for (size_t j = 0; j < ped.name.size(); j++)
+            if (names[c] == sv(ped.name[j])) {
+                row = (int)j;
+                break;
+            }
+        m.ped_row.push_back(row);
+        if (row < 0) continue;
+        m.matched.push_back((int)(c - first));
+        auto it = std::find(m.engine_cols.begin(), m.engine_cols.end(), row);
+        if (it == m.engine_cols.end()) {
+            m.unique.push_back((int)m.engine_cols.size());
+            m.engine_cols.push_back(row);
+        } else
+            m.unique.push_back((int)(it - m.engine_cols.begin()));
+    }
+    return m;
+}
+
+struct Engine {
+    fs_engine *h = nullptr;
+    ~Engine() { fs_destroy(h); }
+    bool create(const PedRows &ped, const ColumnMap &cm, const fs_params &prm, int device) {
+        std::vector<int32_t> id(ped.id.begin(), ped.id.end()), mo(ped.mother_id.begin(), ped.mother_id.end()),
+            fa(ped.father_id.begin(), ped.father_id.end()), ge(ped.gender.begin(), ped.gender.end());
+        fs_pedigree fp{(int32_t)id.size(), id.data(), mo.data(), fa.data(), ge.data(), (int32_t)cm.engine_cols.size(),
+                       cm.engine_cols.data()};
+        if (fs_create(&fp, &prm, device, &h) != FS_OK) {
+            std::cout << fs_last_error() << std::endl;
+            g_engine_failed = true;
+            return false;
+        }
+        return true;
+    }
+};
+
+// One batch of records waiting for the engine.
+struct Pending {
+    std::vector<double> lk;
+    std::vector<uint8_t> flags;
+    std::vector<double> post, single;
+    std::vector<uint8_t> gt, status;
+    size_t count() const { return flags.size(); }
+    void clear() {
+        lk.clear();
+        flags.clear();
+    }
+    bool run(Engine &e, int method, int S, int burn, int rep, unsigned long long seed, long long v_offset) {
+        const size_t V = count();
+        post.resize(V * S * 3);
+        single.resize(V * S * 3);
+        gt.resize(V * S);
+        status.resize(V);
+        const double t0 = now();
+        const int rc = fs_run(e.h, method, (int64_t)V, lk.data(), flags.data(), burn, rep, seed, v_offset, post.data(),
+                              single.data(), gt.data(), status.data());
+        g_stats.engine_s += now() - t0;
+        g_stats.kernel_ms += fs_last_kernel_ms(e.h);
+        g_stats.batches++;
+        if (rc != FS_OK) {
+            std::cout << fs_last_error() << std::endl;
+            g_engine_failed = true;
+            return false;
+        }
+        return true;
+    }
+};
+
+void emit_stats() {
+    if (!std::getenv("FAMSEQ_STATS")) return;
+    std::fprintf(stderr,
+                 "{\"records\": %lld, \"computed\": %lld, \"failed\": %lld, \"batches\": %lld, \"parse_s\": %.4f, "
+                 "\"engine_s\": %.4f, \"kernel_ms\": %.3f, \"write_s\": %.4f, \"total_s\": %.4f}\n",
+                 g_stats.records, g_stats.computed, g_stats.failed, g_stats.batches, g_stats.parse_s, g_stats.engine_s,
+                 g_stats.kernel_ms, g_stats.write_s, g_stats.total_s);
+}
+
+} // namespace
+
+// --------------------------------------------------------------------------------------------------------
+bool read_ped(const std::string &path, PedRows &out) {
+    std::ifstream fin(path.c_str());
+    if (!fin.is_open()) {
+        std::cout << "Cannot open " << path << std::endl;
+        return false;
+    }
+    std::string line;
+    std::getline(fin, line); // one header line
+    out = PedRows();
+    while (!fin.eof()) {
+        std::getline(fin, line);
+        if (line.size() < 2) break;
+        int id = 0, mid = 0, fid = 0, gender = 0;
+        std::string name;
+        std::istringstream in(line);
+        in >> id >> mid >> fid >> gender >> name;
+        out.id.push_back(id);
+        out.mother_id.push_back(mid);
+        out.father_id.push_back(fid);
+        out.gender.push_back(gender);
+        out.name.push_back(name);
+    }
+    return true;
+}
+
+bool check_family(const PedRows &ped) {
+    std::vector<int32_t> id(ped.id.begin(), ped.id.end()), mo(ped.mother_id.begin(), ped.mother_id.end()),
+        fa(ped.father_id.begin(), ped.father_id.end()), ge(ped.gender.begin(), ped.gender.end());
+    fs_pedigree fp{(int32_t)id.size(), id.data(), mo.data(), fa.data(), ge.data(), 0, nullptr};
+    fs_engine *h = nullptr;
+    const int rc = fs_create(&fp, nullptr, -1, &h);
+    fs_destroy(h);
+    if (rc == FS_OK) return true;
+    if (rc == FS_E_GENDER)
+        std::cerr << fs_last_error() << std::endl; // family.cpp:208,213 write to cerr
+    else
+        std::cout << fs_last_error() << std::endl;
+    std::cout << "Cannot initiate family. Please check ped file." << std::endl; // file.cpp:1922
+    return false;
+}
+
+// --------------------------------------------------------------------------------------------------------
+// FamSeq vcf
+// --------------------------------------------------------------------------------------------------------
+namespace {
+
+struct VcfItem {
+    enum Kind : uint8_t { Echo, Compute } kind;
+    sv line;
+};
+
+int chrom_number(sv chrom) { // file.cpp:460-466
+    if (chrom.substr(0, 3) == "chr") return to_int(chrom.substr(3));
+    return to_int(chrom);
+}
+
+bool is_x(sv c) { return c == "X" || c == "chrX" || c == "CHRX"; }
+
+} // namespace
+
+bool run_vcf(const VcfOptions &opt, const PedRows &ped) {
+    const double t_start = now();
+    g_stats = RunStats();
+    const std::string &vcf_name = opt.vcf_files[0];
+    bool var_only = opt.var_only, all_line = opt.all_line;
+    if (opt.diff_only) { // file.cpp:124-128
+        all_line = false;
+        var_only = true;
+    }
+    fs_params prm;
+    Priors pri;
+    fill_params(opt, prm, pri);
+
+    std::string data;
+    if (!read_file(vcf_name, data)) {
+        std::cout << "Cannot open " << vcf_name << std::endl;
+        return false;
+    }
+    FILE *fout = std::fopen(opt.output.c_str(), "wb");
+    if (!fout) {
+        std::cout << "Cannot open " << opt.output << std::endl;
+        return false;
+    }
+    std::string out;
+    out.reserve(1 << 24);
+
+    // ---- pass 1: header echo with a one-line delay, tag injection (file.cpp:143-196) ---------------------
+    auto fs_info_lines = [&]() {
+        out += "##FS mutation rate=";
+        put_number(out, prm.mrate);
+        out += " \n##FS genotype frequency in pupulation (Rare): ";
+        put_triplet(out, pri.n);
+        out += "\n##FS genotype frequency in population (Common): ";
+        put_triplet(out, pri.k);
+        out += "\n##FS genotype frequency for chromosome X of male in population (Rare): ";
+        put_triplet(out, pri.xn);
+        out += "\n##FS genotype frequency for chromosome X of male in population (Common): ";
+        put_triplet(out, pri.xk);
+        out += "\n";
+    };
+    sv title;
+    {
+        bool want_info = true, want_tag = true;
+        Lines in(data);
+        sv line;
+        while (in.next(line)) {
+            if (!line.empty() && line[0] == '#') {
+                if (title.size() > 2) {
+                    out.append(title);
+                    out += '\n';
+                    if (title.substr(2, 6) == "FORMAT" && line.size() >= 2 && line.substr(2, 4) == "INFO" && want_tag) {
+                        out += "##FORMAT=<ID=GPP,Number=G,Type=Integer,Description=\"Normalized, Phred-scaled for posterior "
+                               "probability calculated by individual-based Method\">\n";
+                        out += kFormatLines;
+                        want_tag = false;
+                    }
+                    if (line.size() >= 2 && line.substr(2, 6) == "contig" && want_info) {
+                        fs_info_lines();
+                        want_info = false;
+                    }
+                }
+                title = line;
+                continue;
+            }
+            if (want_tag) {
+                out += "##FORMAT=<ID=GPP,Number=G,Type=Integer,Description=\"Normalized, Phred-scaled for posterior "
+                       "probability calbulated by Single Method\">\n";
+                out += kFormatLines;
+            }
+            if (want_info) fs_info_lines();
+            break;
+        }
+    }
+    std::vector<sv> names;
+    split(title, '\t', names);
+    if (names.size() < 9) {
+        std::cout << "Cannot find the #CHROM header line in " << vcf_name << std::endl;
+        std::fclose(fout);
+        return false;
+    }
+    for (int i = 0; i < 9; i++) {
+        out.append(names[i]);
+        out += '\t';
+    }
+    const ColumnMap cm = map_columns(names, 9, ped);
+    for (int c : cm.matched) {
+        out.append(names[9 + c]);
+        out += '\t';
+    }
+    out += '\n';
+    const int S = (int)cm.engine_cols.size();
+    const int real_num_ind = cm.real_num_ind();
+
+    // ---- optional -l location file (file.cpp:235-298) --------------------------------------------------------
+    std::vector<std::vector<int>> location;
+    const bool use_location = !opt.location_file.empty();
+    if (use_location) {
+        std::string ldata;
+        if (!read_file(opt.location_file, ldata)) {
+            std::cout << "Cannot open " << opt.location_file << std::endl;
+            std::fclose(fout);
+            return false;
+        }
+        location.assign(25, {});
+        Lines in(ldata);
+        sv line;
+        std::vector<sv> f;
+        while (in.next(line)) {
+            if (line.size() < 2) break;
+            split(line, '\t', f);
+            int chr = f[0] == "X" ? 23 : f[0] == "Y" ? 24 : f[0] == "MT" ? 25 : to_int(f[0]);
+            if (chr <= 0 || chr > 25 || f.size() < 2) continue;
+            const int pos = to_int(f[1]);
+            if (pos == 0) continue;
+            location[chr - 1].push_back(pos);
+        }
+        for (auto &v : location) std::sort(v.begin(), v.end());
+    }
+
+    Engine eng;
+    if (!eng.create(ped, cm, prm, opt.device)) {
+        std::fclose(fout);
+        return false;
+    }
+    int burn = opt.num_burn_in, rep = opt.num_rep; // file.cpp:644-656
+    if (burn < 0) burn = 1000 * real_num_ind;
+    if (rep < 0) rep = 20000 * real_num_ind;
+
+    // ---- pass 2: records ---------------------------------------------------------------------------------------
+    std::vector<VcfItem> items;
+    Pending batch;
+    std::vector<sv> col, fmt, sub, pl;
+    long long v_offset = 0;
+    bool ok = true;
+
+    auto echo = [&](const std::vector<sv> &c) { // first nine columns and the matched samples, each followed by a tab
+        for (int i = 0; i < 9; i++) {
+            out.append(c[i]);
+            out += '\t';
+        }
+        for (int m : cm.matched) {
+            out.append(c[9 + m]);
+            out += '\t';
+        }
+        out += '\n';
+    };
+
+    auto flush = [&]() -> bool {
+        if (batch.count() && !batch.run(eng, opt.method, S, burn, rep, opt.seed, v_offset)) return false;
+        const double t0 = now();
+        size_t v = 0;
+        for (const VcfItem &it : items) {
+            split(it.line, '\t', col);
+            if (it.kind == VcfItem::Echo) {
+                echo(col);
+            } else {
+                split(col[8], ':', fmt);
+                for (int i = 0; i < 8; i++) {
+                    out.append(col[i]);
+                    out += '\t';
+                }
+                out.append(col[8]);
+                out += ":GPP:FPP:FGT\t";
+                const bool failed = batch.status[v] != 0;
+                if (failed) { // file.cpp:607-619
+                    std::cout << "Warning: this variant hasn't been calculated: " << std::endl;
+                    std::cout << it.line << std::endl;
+                    g_stats.failed++;
+                }
+                bool any_missing = false;
+                for (int m : cm.matched) any_missing |= col[9 + m].size() < 5;
+                for (size_t k = 0; k < cm.matched.size(); k++) {
+                    const sv field = col[9 + cm.matched[k]];
+                    if (failed) {
+                        out.append(field);
+                        out += ":NA:NA:NA\t";
+                        continue;
+                    }
+                    if (any_missing && field.size() < 5) { // file.cpp:927-933
+                        for (size_t j = 0; j < fmt.size(); j++) out += "NA:";
+                    } else {
+                        out.append(field);
+                        out += ':';
+                    }
+                    const size_t o = (v * S + cm.unique[k]) * 3;
+                    put_calls(out, &batch.single[o], &batch.post[o], batch.gt[v * S + cm.unique[k]]);
+                }
+                out += '\n';
+                v++;
+            }
+            if (out.size() > (1u << 23)) {
+                std::fwrite(out.data(), 1, out.size(), fout);
+                out.clear();
+            }
+        }
+        v_offset += (long long)batch.count();
+        g_stats.computed += (long long)batch.count();
+        items.clear();
+        batch.clear();
+        g_stats.write_s += now() - t0;
+        return true;
+    };
+
+    Lines in(data);
+    sv line;
+    double t_parse = now();
+    while (in.next(line)) {
+        if (line.size() < 2) break;
+        if (line[0] == '#') continue;
+        g_stats.records++;
+        split(line, '\t', col);
+        if (col.size() < 9 + cm.ped_row.size()) continue; // malformed record: the reference would read out of bounds
+        const sv chrom = col[0], ref = col[3], alt = col[4];
+        if (use_location) { // file.cpp:318-360
+            int chr = (chrom == "X" || chrom == "chrX") ? 23 : (chrom == "Y" || chrom == "chrY") ? 24 : chrom == "MT" ? 25 : chrom_number(chrom);
+            if (chr <= 0 || chr > 25) continue;
+            const int pos = to_int(col[1]);
+            if (pos == 0) continue;
+            if (!std::binary_search(location[chr - 1].begin(), location[chr - 1].end(), pos)) continue;
+        }
+        auto skip = [&]() {
+            if (all_line) items.push_back({VcfItem::Echo, line});
+        };
+        if (ref == "." || ref == "-") { skip(); continue; }
+        if (ref.size() != 1 || alt.size() != 1) { skip(); continue; }
+        if (var_only && (alt == "." || alt == "-")) continue;
+        if (chrom == "Y" || chrom == "chrY") { skip(); continue; }
+        if (chrom == "MT") { skip(); continue; }
+        const int chr = chrom_number(chrom);
+        if (!((0 < chr && chr < 23) || is_x(chrom))) { skip(); continue; }
+        const bool known = col[2] != ".";
+        const bool chrx = is_x(chrom);
+        int n_miss = 0;
+        for (int m : cm.matched) n_miss += col[9 + m].size() < 5;
+        if (n_miss == real_num_ind) { skip(); continue; }
+        split(col[8], ':', fmt);
+        int ind_pl = -1;
+        for (size_t i = 0; i < fmt.size(); i++)
+            if (fmt[i] == "PL" || fmt[i] == "GL") ind_pl = (int)i; // the last one wins; GL is decoded like PL
+        if (ind_pl < 0) { // no likelihoods: the record is echoed whatever -a says (file.cpp:541-555)
+            items.push_back({VcfItem::Echo, line});
+            continue;
+        }
+        // likelihoods: pow(10, -|PL|/10); missing or malformed sample fields keep (1,1,1) (file.cpp:565-593, :794-831)
+        const size_t base = batch.lk.size();
+        batch.lk.resize(base + (size_t)S * 3, 1.0);
+        for (size_t k = 0; k < cm.matched.size(); k++) {
+            const sv field = col[9 + cm.matched[k]];
+            double *dst = &batch.lk[base + (size_t)cm.unique[k] * 3];
+            if (n_miss > 0 && field.size() < 5) {
+                dst[0] = dst[1] = dst[2] = 1.0;
+                continue;
+            }
+            split(field, ':', sub);
+            if (sub.size() != fmt.size()) continue;
+            split(sub[ind_pl], ',', pl);
+            for (size_t j = 0; j < 3 && j < pl.size(); j++) dst[j] = std::pow(10.0, -std::fabs(to_double(pl[j])) / 10.0);
+        }
+        batch.flags.push_back((uint8_t)((known ? FS_FLAG_KNOWN : 0) | (chrx ? FS_FLAG_CHRX : 0)));
+        items.push_back({VcfItem::Compute, line});
+        if (batch.count() >= kBatch || items.size() >= 4 * kBatch) {
+            g_stats.parse_s += now() - t_parse;
+            if (!(ok = flush())) break;
+            t_parse = now();
+        }
+    }
+    g_stats.parse_s += now() - t_parse;
+    if (ok) ok = flush();
+    std::fwrite(out.data(), 1, out.size(), fout);
+    std::fclose(fout);
+    g_stats.total_s = now() - t_start;
+    emit_stats();
+    return ok;
+}
+
+// --------------------------------------------------------------------------------------------------------
+// FamSeq LK
+// --------------------------------------------------------------------------------------------------------
+bool run_lk(const LkOptions &opt, const PedRows &ped) {
+    const double t_start = now();
+    g_stats = RunStats();
+    fs_params prm;
+    Priors pri;
+    fill_params(opt, prm, pri);
+    std::string data;
+    if (!read_file(opt.lk_file, data)) {
+        std::cout << "Cannot open " << opt.lk_file << std::endl;
+        return false;
+    }
+    FILE *fout = std::fopen(opt.output.c_str(), "wb");
+    if (!fout) {
+        std::cout << "Cannot open " << opt.output << std::endl;
+        return false;
+    }
+    std::string out;
+    out.reserve(1 << 24);
+    Lines in(data);
+    sv title;
+    in.next(title);
+    // file.cpp:1664-1669
+    out += "##FORMAT=<ID=GPP,Number=G,Type=Integer,Description=\"Normalized, Phred-scaled for posterior probability "
+           "calculated by individual-base Method\">\n";
+    out += kFormatLines;
+    out += "##FS mutation rate=";
+    put_number(out, prm.mrate);
+    out += " \n##FS genotype frequency in pupulation: ";
+    put_triplet(out, pri.n);
+    out += "\n";
+    std::vector<sv> names;
+    split(title, '\t', names);
+    const ColumnMap cm = map_columns(names, 0, ped);
+    out += "#FORMAT\t";
+    for (int c : cm.matched) {
+        out.append(names[c]);
+        out += '\t';
+    }
+    out += '\n';
+    const int S = (int)cm.engine_cols.size();
+
+    Engine eng;
+    if (!eng.create(ped, cm, prm, opt.device)) {
+        std::fclose(fout);
+        return false;
+    }
+
+    std::vector<sv> lines, col, pl;
+    Pending batch;
+    long long v_offset = 0;
+    bool ok = true;
+    auto flush = [&]() -> bool {
+        // the LK driver calls the engine with Known = false, chrType = 0 (file.cpp:1751,1768,1785): flags stay 0
+        if (batch.count() && !batch.run(eng, opt.method, S, opt.num_burn_in, opt.num_rep, opt.seed, v_offset)) return false;
+        const double t0 = now();
+        for (size_t v = 0; v < lines.size(); v++) {
+            split(lines[v], '\t', col);
+            out += "LK:GPP:FPP:FGT\t";
+            const bool failed = batch.status[v] != 0;
+            if (failed) {
+                std::cout << "Warning: this variant hasn't been calculated: " << std::endl;
+                std::cout << lines[v] << std::endl;
+                g_stats.failed++;
+            }
+            for (size_t k = 0; k < cm.matched.size(); k++) {
+                out.append(col[cm.matched[k]]);
+                if (failed) {
+                    out += ":NA:NA:NA\t";
+                    continue;
+                }
+                out += ':';
+                const size_t o = (v * S + cm.unique[k]) * 3;
+                put_calls(out, &batch.single[o], &batch.post[o], batch.gt[v * S + cm.unique[k]]);
+            }
+            out += '\n';
+            if (out.size() > (1u << 23)) {
+                std::fwrite(out.data(), 1, out.size(), fout);
+                out.clear();
+            }
+        }
+        v_offset += (long long)batch.count();
+        g_stats.computed += (long long)batch.count();
+        lines.clear();
+        batch.clear();
+        g_stats.write_s += now() - t0;
+        return true;
+    };
+
+    sv line;
+    double t_parse = now();
+    while (in.next(line)) {
+        if (line.size() < 2) break;
+        g_stats.records++;
+        split(line, '\t', col);
+        if (col.size() < cm.ped_row.size()) continue; // malformed row: the reference would read out of bounds
+        const size_t base = batch.lk.size();
+        batch.lk.resize(base + (size_t)S * 3, 1.0);
+        for (size_t k = 0; k < cm.matched.size(); k++) {
+            double *dst = &batch.lk[base + (size_t)cm.unique[k] * 3];
+            split(col[cm.matched[k]], ',', pl);
+            for (size_t j = 0; j < 3 && j < pl.size(); j++) {
+                const double x = to_double(pl[j]);
+                switch (opt.lk_type) { // file.cpp:1719-1738
+                case 2: dst[j] = std::pow(10.0, x); break;
+                case 3: dst[j] = std::exp(x); break;
+                case 4: dst[j] = std::pow(10.0, -x / 10.0); break;
+                default: dst[j] = x; break;
+                }
+            }
+        }
+        batch.flags.push_back(0);
+        lines.push_back(line);
+        if (batch.count() >= kBatch) {
+            g_stats.parse_s += now() - t_parse;
+            if (!(ok = flush())) break;
+            t_parse = now();
+        }
+    }
+    g_stats.parse_s += now() - t_parse;
+    if (ok) ok = flush();
+    std::fwrite(out.data(), 1, out.size(), fout);
+    std::fclose(fout);
+    g_stats.total_s = now() - t_start;
+    emit_stats();
+    return ok;
+}
+
+} // namespace famseq_cli

@@ -395,3 +395,50 @@ int fs_run(fs_engine *e, int method, int64_t V, const double *lk, const uint8_t 
 }
 
 } // extern "C"
+
+// ---- FP64 roofline probe ----------------------------------------------------------------------------
+// Register-resident DFMA chains (8 independent accumulators per thread): the measured FP64 peak that
+// bench.py uses as the roofline denominator of the BN and MCMC kernels (MEASURED_PEAKS.json has none).
+namespace {
+__global__ void __launch_bounds__(256) fp64_probe_kernel(double *out, int iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-9, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 12345.678) out[0] = s; // never true; keeps the chains alive
+}
+} // namespace
+
+extern "C" int fs_bench_fp64_tflops(int device, double *tflops) {
+    if (!tflops) return fail(FS_E_ARG, "fs_bench_fp64_tflops: null argument");
+    FS_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    FS_CUDA(cudaGetDeviceProperties(&prop, device));
+    double *d = nullptr;
+    FS_CUDA(cudaMalloc(&d, 8));
+    cudaEvent_t e0, e1;
+    FS_CUDA(cudaEventCreate(&e0));
+    FS_CUDA(cudaEventCreate(&e1));
+    const int iters = 4096, blocks = prop.multiProcessorCount * 8;
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        FS_CUDA(cudaEventRecord(e0));
+        fp64_probe_kernel<<<blocks, 256>>>(d, iters, 1.0000001, 1e-9);
+        FS_CUDA(cudaEventRecord(e1));
+        FS_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        FS_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 64.0 * iters * 256.0 * blocks;
+        if (rep > 0 && ms > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    *tflops = best;
+    return FS_OK;
+}

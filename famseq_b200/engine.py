@@ -96,13 +96,15 @@ def lib() -> ctypes.CDLL:
         L.fs_free_pinned.argtypes = [P]
         L.fs_last_kernel_ms.restype = D
         L.fs_last_kernel_ms.argtypes = [P]
+        L.fs_bench_fp64_tflops.restype = ctypes.c_int
+        L.fs_bench_fp64_tflops.argtypes = [ctypes.c_int, P]
         _lib = L
     return _lib
 
 
 EXPORTED_SYMBOLS = ["fs_default_params", "fs_device_count", "fs_create", "fs_destroy", "fs_last_error", "fs_run",
                     "fs_run_device", "fs_get_info", "fs_get_tables", "fs_alloc_pinned", "fs_free_pinned",
-                    "fs_last_kernel_ms"]
+                    "fs_last_kernel_ms", "fs_bench_fp64_tflops"]
 
 
 def _check(rc: int) -> None:
@@ -219,3 +221,10 @@ class Engine:
 
 def device_count() -> int:
     return int(lib().fs_device_count())
+
+
+def measure_fp64_tflops(device: int = 0) -> float:
+    """Plain FP64 (DFMA) throughput of the device, measured by fs_bench_fp64_tflops."""
+    out = ctypes.c_double(0.0)
+    _check(lib().fs_bench_fp64_tflops(device, ctypes.byref(out)))
+    return float(out.value)

@@ -138,6 +138,10 @@ void fs_free_pinned(void *p);
 /* Milliseconds the kernels of the last fs_run on this engine spent on the device (CUDA events). */
 double fs_last_kernel_ms(const fs_engine *e);
 
+/* Measures the device's plain (non-tensor) FP64 throughput with register-resident DFMA chains and writes
+ * TFLOP/s to *tflops.  bench.py uses it as the roofline denominator of the BN and MCMC kernels. */
+int fs_bench_fp64_tflops(int device, double *tflops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -194,8 +194,10 @@ def test_mcmc_converges_to_exact_bn():
         exact = e.run(fs.BN, lk, fl).post
         runs = np.stack([e.run(fs.MCMC, lk, fl, burn=200, rep=4000, seed=k).post for k in range(16)])
     mean, se = runs.mean(0), runs.std(0, ddof=1) / 4.0
-    z = np.abs(mean - exact) / (se + 1e-9)
-    assert np.quantile(z, 0.99) < 5.0 and np.abs(mean - exact).max() < 0.02
+    # entries whose conditional never changes along the chain have a zero seed-to-seed spread and a tiny bias
+    # from the states the chain never visits, hence the 1e-4 floor on the standard error
+    z = np.abs(mean - exact) / (se + 1e-4)
+    assert np.quantile(z, 0.99) < 5.0 and np.abs(mean - exact).max() < 0.01
 
 
 # ------------------------------------------------------------------------------------------------------
