@@ -60,8 +60,52 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index, self.proc, self.lines = index, None, []
+        self.nvml = None
+        self.samples = []  # (sm_mhz, max_mhz, reasons bitmask) polled through NVML every ~1 ms
+        self._stop = False
+        self._max = None
+        self.error = None
+
+    def sample_now(self):
+        """One synchronous NVML sample (called by the timing loop while the kernels are in flight)."""
+        if self.nvml is None:
+            return
+        import pynvml as nv
+
+        h = self.nvml
+        try:
+            if self._max is None:
+                self._max = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        except Exception as ex:  # noqa: BLE001
+            self.error = repr(ex)
+            return
+        try:
+            reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:  # noqa: BLE001
+            try:
+                reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            except Exception as ex:  # noqa: BLE001
+                self.error = repr(ex)
+                reasons = 0
+        self.samples.append((sm, self._max, reasons))
+
+    def _poll(self):
+        while not self._stop:
+            self.sample_now()
+            time.sleep(0.001)
 
     def __enter__(self):
+        try:  # NVML polling catches regions of a few milliseconds that an nvidia-smi loop would miss
+            import pynvml as nv
+
+            nv.nvmlInit()
+            self.nvml = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return self
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
@@ -73,12 +117,26 @@ class ClockSampler:
         return self
 
     def __exit__(self, *a):
+        if self.nvml is not None:
+            self._stop = True
+            self.t.join(timeout=2)
+            return
         if self.proc:
             time.sleep(0.12)
             self.proc.terminate()
             self.t.join(timeout=2)
 
     def summary(self):
+        if self.nvml is not None and self.samples:
+            import pynvml as nv
+
+            bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+            seen = 0
+            for s in self.samples:
+                seen |= s[2]
+            return {"sm_mhz": int(statistics.median(s[0] for s in self.samples)), "sm_max_mhz": int(self.samples[0][1]),
+                    "reasons": sorted(k for k, b in bits.items() if seen & b), "samples": len(self.samples), "source": "nvml"}
         sm, mx, reasons = [], [], set()
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
@@ -89,7 +147,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "error": self.error}
         return {"sm_mhz": int(statistics.median(sm)), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
@@ -194,6 +252,7 @@ def time_device_path(torch, dist, fs, eng, wl: Workload, rank, world, steps, war
         for _ in range(steps):
             step()
         e1.record(stream)
+        clk.sample_now()  # the launches above are asynchronous: this sample is taken while they run
         torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -328,7 +387,7 @@ def main():
         "dtype": "f64", "data": "synthetic", "config": config,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_variant": algorithmic_bytes(3),
-                     "kernel": "es_kernel<128>"},
+                     "kernel": "es_nuclear_kernel<1,128> (TMA bulk load/store, register-resident peeling)"},
         "e2e": {"value": world * args.variants / e2e_s, "unit": "variants/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s * 1e3, "api": "fs_run() on pinned host buffers", "matches_device_path": same},
         "gpu_launches": launches, "clocks": clocks, "failed_variants": failed,

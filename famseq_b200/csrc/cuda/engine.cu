@@ -59,6 +59,9 @@ struct fs_engine {
     int es_rc = FS_OK;
     std::string es_err;
     int es_tb = 0;
+    NuclearParams nuclear;      // register-resident fast path for (father, mother, <= 3 childless children)
+    bool is_nuclear = false;
+    bool force_generic_es = false; // FAMSEQ_ES_GENERIC=1: run nuclear families through the message-program interpreter too
 
     BnParams bn;
     int bn_rc = FS_OK;
@@ -179,6 +182,36 @@ int fs_create(const fs_pedigree *ped, const fs_params *params, int device, fs_en
     // ---- pedigree compilers ----------------------------------------------------------------------
     e->es.C = C;
     e->es_rc = compile_es_program(e->ped, e->es.prog, e->es_err);
+    { // nuclear family: exactly two founders who are the parents of every other member, nobody else has children
+        const Pedigree &p = e->ped;
+        int father = -1, mother = -1;
+        bool ok = p.n >= 3 && p.n <= 2 + ES_NUCLEAR_MAX_CHILDREN && p.n_founders() == 2;
+        for (int i = 0; ok && i < p.n; i++)
+            if (!p.founder(i)) {
+                if (father < 0) {
+                    father = p.father[i];
+                    mother = p.mother[i];
+                }
+                ok = p.father[i] == father && p.mother[i] == mother && p.children[i].empty();
+            }
+        ok = ok && father >= 0 && p.founder(father) && p.founder(mother);
+        if (ok) {
+            NuclearParams &np = e->nuclear;
+            std::memset(&np, 0, sizeof np);
+            np.C = C;
+            np.col_father = p.col_of[father];
+            np.col_mother = p.col_of[mother];
+            for (int i = 0; i < p.n; i++)
+                if (!p.founder(i)) {
+                    np.col_child[np.n_children] = p.col_of[i];
+                    np.male_child[np.n_children] = p.male[i];
+                    np.n_children++;
+                }
+            e->is_nuclear = true;
+        }
+        const char *env = std::getenv("FAMSEQ_ES_GENERIC");
+        e->force_generic_es = env && env[0] == '1';
+    }
     e->bn.C = C;
     e->bn_rc = build_bn_plan(e->ped, e->bn.plan, e->bn_err);
     e->mcmc.C = C;
@@ -274,7 +307,11 @@ static int dispatch(fs_engine *e, int method, const BatchPtrs &B, int32_t burn, 
     switch (method) {
     case FS_METHOD_ES: {
         if (e->es_rc != FS_OK) return fail(e->es_rc, e->es_err);
-        FS_CUDA(launch_es(e->es, B, e->es_tb, stream));
+        const bool tma_ok = ((reinterpret_cast<uintptr_t>(B.gt) | reinterpret_cast<uintptr_t>(B.status)) & 15u) == 0;
+        if (e->is_nuclear && tma_ok && !e->force_generic_es)
+            FS_CUDA(launch_es_nuclear(e->nuclear, B, stream));
+        else
+            FS_CUDA(launch_es(e->es, B, e->es_tb, stream));
         break;
     }
     case FS_METHOD_BN: {

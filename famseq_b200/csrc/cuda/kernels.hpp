@@ -21,6 +21,17 @@ size_t es_smem_bytes(const EsParams &P, int tb);
 int es_pick_block(const EsParams &P, size_t smem_limit);
 cudaError_t launch_es(const EsParams &P, const BatchPtrs &B, int tb, cudaStream_t stream);
 
+// ---- Elston-Stewart, nuclear families (es_nuclear_kernel.cu) -------------------------------------------
+constexpr int ES_NUCLEAR_MAX_CHILDREN = 3;
+struct NuclearParams {
+    RunConstants C;
+    int32_t n_children;
+    int32_t col_father, col_mother;               // input column or -1
+    int32_t col_child[ES_NUCLEAR_MAX_CHILDREN];   // children in ped order
+    int32_t male_child[ES_NUCLEAR_MAX_CHILDREN];
+};
+cudaError_t launch_es_nuclear(const NuclearParams &P, const BatchPtrs &B, cudaStream_t stream);
+
 // ---- Bayesian network (bn_kernel.cu) --------------------------------------------------------------
 struct BnParams {
     RunConstants C;

@@ -253,3 +253,77 @@ def test_device_resident_path_matches_host_path():
         assert e.info()["kernel_launches"] >= 2
     assert np.array_equal(d_post.cpu().numpy(), host.post) and np.array_equal(d_gt.cpu().numpy(), host.gt)
     assert np.array_equal(d_single.cpu().numpy(), host.single) and np.array_equal(d_st.cpu().numpy(), host.status)
+
+
+# ------------------------------------------------------------------------------------------------------
+# nuclear-family fast path (es_nuclear_kernel.cu)
+# ------------------------------------------------------------------------------------------------------
+def _wide_likelihoods(V, S, seed):
+    """Random mantissas over a wide exponent range (incl. subnormal and zero entries): stresses the shared-reciprocal
+    division of the fast path, which must return the IEEE quotient bit for bit."""
+    rng = np.random.default_rng(seed)
+    lk = rng.random((V, S, 3)) * np.exp2(rng.integers(-1040, 1, (V, S, 3)).astype(np.float64))
+    lk[rng.random((V, S, 3)) < 0.02] = 0.0
+    lk[rng.random((V, S)) < 0.05] = 1.0
+    return lk
+
+
+@pytest.mark.parametrize("n_children", [1, 2, 3])
+def test_nuclear_fast_path_is_bit_identical(n_children, monkeypatch):
+    rows = [(1, 0, 0, 1), (2, 0, 0, 2)] + [(3 + k, 2, 1, 1 + k % 2) for k in range(n_children)]
+    ped = synth._mk(rows)
+    V = 400_000 if n_children == 1 else 100_000
+    lk, fl = synth.synth_likelihoods(ped, V, seed=50 + n_children, x_fraction=0.3)
+    wide = _wide_likelihoods(V, ped.n, 60 + n_children)
+    lk = np.concatenate([lk, wide])
+    fl = np.concatenate([fl, fl])
+    want = O.run(ped, ped.sequenced_cols(), lk, fl, method=O.ES)
+    with engine_for(ped) as e:
+        got = e.run(fs.ES, lk, fl)
+    assert_parity(got, want, 0.0, f"nuclear C={n_children}")
+    ok = want["status"] == 0
+    assert np.array_equal(got.post[ok], want["post"][ok]) and np.array_equal(got.single[ok], want["single"][ok])
+    assert 0 < (~ok).sum() < len(ok)
+    # the message-program interpreter must give the same bytes for the same pedigree
+    monkeypatch.setenv("FAMSEQ_ES_GENERIC", "1")
+    with engine_for(ped) as e:
+        gen = e.run(fs.ES, lk[:50_000], fl[:50_000])
+    assert np.array_equal(gen.post, got.post[:50_000]) and np.array_equal(gen.gt, got.gt[:50_000])
+    assert np.array_equal(gen.status, got.status[:50_000])
+
+
+def test_nuclear_partial_sequencing_and_permuted_rows():
+    # children listed before their parents, the father unsequenced, input columns in another order
+    rows = [(7, 5, 9, 2), (9, 0, 0, 1), (4, 5, 9, 1), (5, 0, 0, 2)]
+    ped = synth._mk(rows)
+    cols = [3, 0, 2]
+    lk = _wide_likelihoods(20_000, 3, 77)
+    lk2, fl = synth.synth_likelihoods(synth.trio(), 20_000, seed=78, x_fraction=0.5)
+    for data in (lk, lk2):
+        want = O.run(ped, cols, data, fl, method=O.ES)
+        with engine_for(ped, cols) as e:
+            got = e.run(fs.ES, data, fl)
+        assert_parity(got, want, 0.0, "nuclear/partial")
+        ok = want["status"] == 0
+        assert np.array_equal(got.post[ok], want["post"][ok])
+
+
+def test_lrc_gate_shortcut_matches_division():
+    """-LRC 1 takes the big < sum shortcut in the nuclear kernel; other values divide.  Likelihood rows whose largest
+    entry is within a few ulps of the row sum are the cases where the two could differ."""
+    ped = synth.trio()
+    rng = np.random.default_rng(5)
+    V = 50_000
+    lk = np.zeros((V, 3, 3))
+    lk[:, :, 0] = rng.random((V, 3))
+    tiny = np.exp2(rng.integers(-1074, -40, (V, 3)).astype(np.float64))
+    lk[:, :, 1] = lk[:, :, 0] * tiny * (rng.random((V, 3)) < 0.7)
+    lk[:, :, 2] = 0.0
+    for lc in (1.0, 0.999999999):
+        prm = fs.Params.default()
+        prm.lrc = lc
+        want = O.run(ped, ped.sequenced_cols(), lk, None, method=O.ES, lc=lc)
+        with engine_for(ped, params=prm) as e:
+            got = e.run(fs.ES, lk, None)
+        assert_parity(got, want, 0.0, f"lrc gate {lc}")
+        assert np.array_equal(got.post, want["post"])
