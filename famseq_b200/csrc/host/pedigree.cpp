@@ -89,8 +89,14 @@ int build_pedigree(int n, const int32_t *id, const int32_t *mother_id, const int
             err = "fs_pedigree.cols entry out of range";
             return FS_E_ARG;
         }
+        if (p.col_of[cols[c]] >= 0) {
+            // two input columns with the same sample name: the reference lets the later column overwrite the
+            // earlier one's likelihoods; the command line resolves that before calling the engine
+            err = "fs_pedigree.cols lists ped row " + std::to_string(cols[c]) + " twice";
+            return FS_E_ARG;
+        }
         p.cols.push_back(cols[c]);
-        p.col_of[cols[c]] = c; // a later column matching the same row overwrites, as mapP2V does
+        p.col_of[cols[c]] = c;
     }
 
     // Loop detection on the marriage-node graph: one node per member, one per couple; edges

@@ -63,7 +63,8 @@ typedef struct fs_pedigree {
     const int32_t *father_id; /* [n]                                                                  */
     const int32_t *gender;    /* [n] 1 male, 2 female (anything else is treated as "not male")        */
     int32_t s;                /* sequenced input columns that matched a ped row                       */
-    const int32_t *cols;      /* [s] ped row of each matched input column, in input-column order      */
+    const int32_t *cols;      /* [s] ped row of each matched input column, in input-column order;
+                               *     every ped row at most once                                        */
 } fs_pedigree;
 
 typedef struct fs_params {
