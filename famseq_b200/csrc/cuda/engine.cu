@@ -322,7 +322,7 @@ static int dispatch(fs_engine *e, int method, const BatchPtrs &B, int32_t burn, 
     case FS_METHOD_MCMC: {
         if (e->mcmc_rc != FS_OK) return fail(e->mcmc_rc, e->mcmc_err);
         if (burn < 0 || rep <= 0) return fail(FS_E_ARG, "MCMC needs burn >= 0 and rep >= 1");
-        FS_CUDA(launch_mcmc(e->mcmc, B, e->mcmc_tb, burn, rep, seed, v_offset, stream));
+        FS_CUDA(launch_mcmc(e->mcmc, B, e->mcmc_tb, burn, rep, seed, v_offset, e->sm_count, stream));
         break;
     }
     default:

@@ -1,4 +1,5 @@
 // bn_plan.cpp -- see bn_plan.hpp.
+#include <cstdlib>
 #include <cstring>
 
 #include "../../../include/famseq_b200.h"
@@ -44,6 +45,10 @@ int build_bn_plan(const Pedigree &ped, BnPlan &out, std::string &err) {
     for (int L = 0; L < N; L++) level_of[order[L]] = L;
 
     p.u = N < 3 ? N : (N >= 9 ? BN_MAX_UNROLL : 3);
+    if (const char *env = std::getenv("FAMSEQ_BN_UNROLL")) { // tuning knob: depth of the fully unrolled block
+        const int u = std::atoi(env);
+        if (u >= 1 && u <= BN_MAX_UNROLL && u <= N) p.u = u;
+    }
     p.h = N - p.u < 5 ? N - p.u : 5;
     p.r = N - p.u - p.h;
     p.group = 1;

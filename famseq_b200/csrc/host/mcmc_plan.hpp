@@ -1,6 +1,7 @@
 // mcmc_plan.hpp -- neighbour lists for the single-site Gibbs sampler (family::estGenoProb,
 // src/family.cpp:2098-2299): for every member, in ped order, its parents and the (child, other parent)
-// pairs whose transmission factors enter its full conditional.
+// pairs whose transmission factors enter its full conditional, packed into one descriptor word per member
+// and per link so that a Gibbs step needs one uniform constant load for each.
 // Shared between host/mcmc_plan.cpp and cuda/mcmc_kernel.cu.
 #pragma once
 
@@ -9,18 +10,16 @@
 namespace famseq {
 
 constexpr int MCMC_MAX_MEMBERS = 64; // genotype vector packed 2 bits/member in two 64-bit registers
-constexpr int MCMC_MAX_LINKS = 512;
+constexpr int MCMC_MAX_LINKS = 255;
 
+// member descriptor: bits 0-5 mother, 6-11 father, 12 founder, 13 male, 14-21 first link, 22-29 link count
+// link descriptor  : bits 0-5 child, 6-11 the child's other parent, 12 child is male
 struct McmcPlan {
     int32_t n = 0;
     int32_t n_links = 0;
-    int8_t mother[MCMC_MAX_MEMBERS]; // -1 for founders
-    int8_t father[MCMC_MAX_MEMBERS];
-    uint8_t male[MCMC_MAX_MEMBERS];
-    int16_t col[MCMC_MAX_MEMBERS];        // input column or -1
-    uint16_t link_begin[MCMC_MAX_MEMBERS + 1]; // links of member i: [link_begin[i], link_begin[i+1])
-    uint8_t link_child[MCMC_MAX_LINKS];
-    uint8_t link_other[MCMC_MAX_LINKS]; // the child's other parent
+    uint32_t member[MCMC_MAX_MEMBERS];
+    uint16_t link[MCMC_MAX_LINKS + 1];
+    int16_t col[MCMC_MAX_MEMBERS]; // input column or -1
 };
 
 } // namespace famseq

@@ -452,44 +452,48 @@ void fso_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4
     out[3] = c3;
 }
 
+/* Random numbers.  LIBC: rand(), exactly the reference's calls in the reference's order.  PHILOX: the word of
+ * member i in sweep s of global site gv is word i%4 of Philox4x32-10(counter = (s, i/4, gv_lo, gv_hi), key = seed);
+ * s = 0 initialises the genotypes, s >= 1 are the sweeps.  The CUDA kernel uses the same indexing, so a value
+ * depends on (seed, site, sweep, member) only and not on the order in which members are visited. */
 typedef struct {
     int kind;
-    uint32_t key[2], ctr[4], buf[4];
-    int have;
+    uint32_t key[2], gv[2];
+    uint32_t buf[4];
+    int64_t buf_sweep, buf_block; /* which Philox block `buf` holds */
 } rng_t;
 
 static void rng_start(rng_t *r, int kind, int64_t seed, int64_t gv) {
     r->kind = kind;
     r->key[0] = (uint32_t)((uint64_t)seed & 0xffffffffu);
     r->key[1] = (uint32_t)((uint64_t)seed >> 32);
-    r->ctr[0] = 0;
-    r->ctr[1] = 0;
-    r->ctr[2] = (uint32_t)((uint64_t)gv & 0xffffffffu);
-    r->ctr[3] = (uint32_t)((uint64_t)gv >> 32);
-    r->have = 0;
+    r->gv[0] = (uint32_t)((uint64_t)gv & 0xffffffffu);
+    r->gv[1] = (uint32_t)((uint64_t)gv >> 32);
+    r->buf_sweep = r->buf_block = -1;
 }
 
-static uint32_t rng_u32(rng_t *r) {
-    if (r->have == 0) {
-        fso_philox4x32(r->ctr, r->key, r->buf);
-        r->ctr[0]++;
-        r->have = 4;
+static uint32_t rng_u32(rng_t *r, int sweep, int member) {
+    if (r->buf_sweep != sweep || r->buf_block != member / 4) {
+        const uint32_t ctr[4] = {(uint32_t)sweep, (uint32_t)(member / 4), r->gv[0], r->gv[1]};
+        fso_philox4x32(ctr, r->key, r->buf);
+        r->buf_sweep = sweep;
+        r->buf_block = member / 4;
     }
-    return r->buf[4 - r->have--];
+    return r->buf[member % 4];
 }
 
-static int rng_init_genotype(rng_t *r) {
+static int rng_init_genotype(rng_t *r, int member) {
     if (r->kind == FSO_RNG_LIBC) return rand() % 3; /* family.cpp:2063-2067 */
-    return (int)(rng_u32(r) % 3u);
+    return (int)(rng_u32(r, 0, member) % 3u);
 }
 
-static double rng_uniform(rng_t *r) {
+static double rng_uniform(rng_t *r, int sweep, int member) {
     if (r->kind == FSO_RNG_LIBC) return (double)rand() / (double)RAND_MAX; /* family.cpp:2161 */
-    return ((double)rng_u32(r) + 0.5) * (1.0 / 4294967296.0);
+    return ((double)rng_u32(r, sweep, member) + 0.5) * (1.0 / 4294967296.0);
 }
 
 /* one sweep over all individuals in ped order */
-static void gibbs_sweep(const fam_t *f, int *cur, double *acc, int known, int chrx, rng_t *rng) {
+static void gibbs_sweep(const fam_t *f, int *cur, double *acc, int known, int chrx, rng_t *rng, int sweep) {
     const int N = f->N;
     for (int i = 0; i < N; i++) {
         double w[3] = {1000000, 1000000, 1000000};
@@ -516,7 +520,7 @@ static void gibbs_sweep(const fam_t *f, int *cur, double *acc, int known, int ch
             w[0] = w[1] = w[2] = 0;
         else
             for (int g = 0; g < 3; g++) w[g] = w[g] / s;
-        double rd = rng_uniform(rng);
+        double rd = rng_uniform(rng, sweep, i);
         if (rd < w[0])
             cur[i] = 0;
         else if (rd > (1.0 - w[2]))
@@ -531,10 +535,10 @@ static int run_mcmc(fam_t *f, int known, int chrx, int burn, int rep, rng_t *rng
     const int N = f->N;
     int *cur = (int *)calloc(N, sizeof(int));
     double *acc = (double *)calloc((size_t)N * 3, sizeof(double));
-    for (int i = 0; i < N; i++) cur[i] = rng_init_genotype(rng);
-    for (int t = 0; t < burn; t++) gibbs_sweep(f, cur, acc, known, chrx, rng);
+    for (int i = 0; i < N; i++) cur[i] = rng_init_genotype(rng, i);
+    for (int t = 0; t < burn; t++) gibbs_sweep(f, cur, acc, known, chrx, rng, 1 + t);
     memset(acc, 0, sizeof(double) * N * 3);
-    for (int t = 0; t < rep; t++) gibbs_sweep(f, cur, acc, known, chrx, rng);
+    for (int t = 0; t < rep; t++) gibbs_sweep(f, cur, acc, known, chrx, rng, 1 + burn + t);
     int ok = 1;
     for (int i = 0; i < N && ok; i++) {
         for (int g = 0; g < 3; g++) f->post[i * 3 + g] = acc[i * 3 + g] / rep;

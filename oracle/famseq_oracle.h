@@ -42,7 +42,7 @@ void fso_tables(double mrate, double *pcp2, double *pcp2xf, double *pcp2xm);
  *  flags[v]  : bit0 Known, bit1 chrX
  *  lk        : [V][S][3] raw likelihoods; unsequenced members are (1,1,1)
  *  rng_kind  : MCMC only. LIBC = rand() exactly as the reference (srand(seed) first if seed >= 0);
- *              PHILOX = counter-based stream keyed (seed, v_offset + v), identical to the CUDA kernel
+ *              PHILOX = counter-based: word i%4 of Philox(counter (sweep, i/4, site), key seed), as the CUDA kernel
  *  post/single [V][S][3], gt [V][S], status[V] (1 = the reference would have returned false);
  *  post_full/single_full [V][N][3] may be NULL.
  * Returns 0 or a negative FSO_E_* code. */
