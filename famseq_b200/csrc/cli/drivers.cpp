@@ -18,6 +18,7 @@
 #include <limits>
 #include <sstream>
 #include <string_view>
+#include <thread>
 
 #include "../../../include/famseq_b200.h"
 
@@ -237,6 +238,20 @@ struct Pending {
     }
 };
 
+// Number of host threads for parsing / formatting: FAMSEQ_THREADS or the hardware concurrency (at most 64).
+int host_threads() {
+    int n = (int)std::thread::hardware_concurrency();
+    if (const char *env = std::getenv("FAMSEQ_THREADS")) n = std::atoi(env);
+    return std::max(1, std::min(n, 64));
+}
+
+template <class F> void run_parallel(int n, F f) {
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n; t++) pool.emplace_back(f, t);
+    f(0);
+    for (auto &th : pool) th.join();
+}
+
 void emit_stats() {
     if (!std::getenv("FAMSEQ_STATS")) return;
     std::fprintf(stderr,
@@ -438,146 +453,192 @@ bool run_vcf(const VcfOptions &opt, const PedRows &ped) {
     if (rep < 0) rep = 20000 * real_num_ind;
 
     // ---- pass 2: records ---------------------------------------------------------------------------------------
-    std::vector<VcfItem> items;
+    // Blocks of up to kBatch record lines.  Parsing (tokenise, skip rules, PL -> likelihood) and formatting
+    // (Phred encode, "%g") are spread over host threads, each owning a contiguous range of the block; the engine
+    // call in between sees one batch.  Output order is the input order.
+    struct Part {
+        std::vector<VcfItem> items;
+        std::vector<double> lk;
+        std::vector<uint8_t> flags;
+        std::string out, warn;
+        long long failed = 0;
+        size_t first = 0; // index of this part's first computed variant inside the batch
+    };
+    const int n_threads = host_threads();
+    std::vector<Part> parts((size_t)n_threads);
     Pending batch;
-    std::vector<sv> col, fmt, sub, pl;
     long long v_offset = 0;
     bool ok = true;
 
-    auto echo = [&](const std::vector<sv> &c) { // first nine columns and the matched samples, each followed by a tab
-        for (int i = 0; i < 9; i++) {
-            out.append(c[i]);
-            out += '\t';
-        }
-        for (int m : cm.matched) {
-            out.append(c[9 + m]);
-            out += '\t';
-        }
-        out += '\n';
-    };
-
-    auto flush = [&]() -> bool {
-        if (batch.count() && !batch.run(eng, opt.method, S, burn, rep, opt.seed, v_offset)) return false;
-        const double t0 = now();
-        size_t v = 0;
-        for (const VcfItem &it : items) {
-            split(it.line, '\t', col);
-            if (it.kind == VcfItem::Echo) {
-                echo(col);
-            } else {
-                split(col[8], ':', fmt);
-                for (int i = 0; i < 8; i++) {
-                    out.append(col[i]);
-                    out += '\t';
-                }
-                out.append(col[8]);
-                out += ":GPP:FPP:FGT\t";
-                const bool failed = batch.status[v] != 0;
-                if (failed) { // file.cpp:607-619
-                    std::cout << "Warning: this variant hasn't been calculated: " << std::endl;
-                    std::cout << it.line << std::endl;
-                    g_stats.failed++;
-                }
-                bool any_missing = false;
-                for (int m : cm.matched) any_missing |= col[9 + m].size() < 5;
-                for (size_t k = 0; k < cm.matched.size(); k++) {
-                    const sv field = col[9 + cm.matched[k]];
-                    if (failed) {
-                        out.append(field);
-                        out += ":NA:NA:NA\t";
-                        continue;
-                    }
-                    if (any_missing && field.size() < 5) { // file.cpp:927-933
-                        for (size_t j = 0; j < fmt.size(); j++) out += "NA:";
-                    } else {
-                        out.append(field);
-                        out += ':';
-                    }
-                    const size_t o = (v * S + cm.unique[k]) * 3;
-                    put_calls(out, &batch.single[o], &batch.post[o], batch.gt[v * S + cm.unique[k]]);
-                }
-                out += '\n';
-                v++;
+    auto parse_range = [&](Part &P, const sv *lines, size_t n) {
+        std::vector<sv> col, fmt, sub, pl;
+        P.items.clear();
+        P.lk.clear();
+        P.flags.clear();
+        for (size_t li = 0; li < n; li++) {
+            const sv line = lines[li];
+            split(line, '\t', col);
+            if (col.size() < 9 + cm.ped_row.size()) continue; // malformed record: the reference would read out of bounds
+            const sv chrom = col[0], ref = col[3], alt = col[4];
+            if (use_location) { // file.cpp:318-360
+                int chr = (chrom == "X" || chrom == "chrX") ? 23 : (chrom == "Y" || chrom == "chrY") ? 24 : chrom == "MT" ? 25 : chrom_number(chrom);
+                if (chr <= 0 || chr > 25) continue;
+                const int pos = to_int(col[1]);
+                if (pos == 0) continue;
+                if (!std::binary_search(location[chr - 1].begin(), location[chr - 1].end(), pos)) continue;
             }
-            if (out.size() > (1u << 23)) {
-                std::fwrite(out.data(), 1, out.size(), fout);
-                out.clear();
-            }
-        }
-        v_offset += (long long)batch.count();
-        g_stats.computed += (long long)batch.count();
-        items.clear();
-        batch.clear();
-        g_stats.write_s += now() - t0;
-        return true;
-    };
-
-    Lines in(data);
-    sv line;
-    double t_parse = now();
-    while (in.next(line)) {
-        if (line.size() < 2) break;
-        if (line[0] == '#') continue;
-        g_stats.records++;
-        split(line, '\t', col);
-        if (col.size() < 9 + cm.ped_row.size()) continue; // malformed record: the reference would read out of bounds
-        const sv chrom = col[0], ref = col[3], alt = col[4];
-        if (use_location) { // file.cpp:318-360
-            int chr = (chrom == "X" || chrom == "chrX") ? 23 : (chrom == "Y" || chrom == "chrY") ? 24 : chrom == "MT" ? 25 : chrom_number(chrom);
-            if (chr <= 0 || chr > 25) continue;
-            const int pos = to_int(col[1]);
-            if (pos == 0) continue;
-            if (!std::binary_search(location[chr - 1].begin(), location[chr - 1].end(), pos)) continue;
-        }
-        auto skip = [&]() {
-            if (all_line) items.push_back({VcfItem::Echo, line});
-        };
-        if (ref == "." || ref == "-") { skip(); continue; }
-        if (ref.size() != 1 || alt.size() != 1) { skip(); continue; }
-        if (var_only && (alt == "." || alt == "-")) continue;
-        if (chrom == "Y" || chrom == "chrY") { skip(); continue; }
-        if (chrom == "MT") { skip(); continue; }
-        const int chr = chrom_number(chrom);
-        if (!((0 < chr && chr < 23) || is_x(chrom))) { skip(); continue; }
-        const bool known = col[2] != ".";
-        const bool chrx = is_x(chrom);
-        int n_miss = 0;
-        for (int m : cm.matched) n_miss += col[9 + m].size() < 5;
-        if (n_miss == real_num_ind) { skip(); continue; }
-        split(col[8], ':', fmt);
-        int ind_pl = -1;
-        for (size_t i = 0; i < fmt.size(); i++)
-            if (fmt[i] == "PL" || fmt[i] == "GL") ind_pl = (int)i; // the last one wins; GL is decoded like PL
-        if (ind_pl < 0) { // no likelihoods: the record is echoed whatever -a says (file.cpp:541-555)
-            items.push_back({VcfItem::Echo, line});
-            continue;
-        }
-        // likelihoods: pow(10, -|PL|/10); missing or malformed sample fields keep (1,1,1) (file.cpp:565-593, :794-831)
-        const size_t base = batch.lk.size();
-        batch.lk.resize(base + (size_t)S * 3, 1.0);
-        for (size_t k = 0; k < cm.matched.size(); k++) {
-            const sv field = col[9 + cm.matched[k]];
-            double *dst = &batch.lk[base + (size_t)cm.unique[k] * 3];
-            if (n_miss > 0 && field.size() < 5) {
-                dst[0] = dst[1] = dst[2] = 1.0;
+            auto skip = [&]() {
+                if (all_line) P.items.push_back({VcfItem::Echo, line});
+            };
+            if (ref == "." || ref == "-") { skip(); continue; }
+            if (ref.size() != 1 || alt.size() != 1) { skip(); continue; }
+            if (var_only && (alt == "." || alt == "-")) continue;
+            if (chrom == "Y" || chrom == "chrY") { skip(); continue; }
+            if (chrom == "MT") { skip(); continue; }
+            const int chr = chrom_number(chrom);
+            if (!((0 < chr && chr < 23) || is_x(chrom))) { skip(); continue; }
+            const bool known = col[2] != ".";
+            const bool chrx = is_x(chrom);
+            int n_miss = 0;
+            for (int m : cm.matched) n_miss += col[9 + m].size() < 5;
+            if (n_miss == real_num_ind) { skip(); continue; }
+            split(col[8], ':', fmt);
+            int ind_pl = -1;
+            for (size_t i = 0; i < fmt.size(); i++)
+                if (fmt[i] == "PL" || fmt[i] == "GL") ind_pl = (int)i; // the last one wins; GL is decoded like PL
+            if (ind_pl < 0) { // no likelihoods: the record is echoed whatever -a says (file.cpp:541-555)
+                P.items.push_back({VcfItem::Echo, line});
                 continue;
             }
-            split(field, ':', sub);
-            if (sub.size() != fmt.size()) continue;
-            split(sub[ind_pl], ',', pl);
-            for (size_t j = 0; j < 3 && j < pl.size(); j++) dst[j] = std::pow(10.0, -std::fabs(to_double(pl[j])) / 10.0);
+            // likelihoods: pow(10, -|PL|/10); missing or malformed sample fields keep (1,1,1) (file.cpp:565-593, :794-831)
+            const size_t base = P.lk.size();
+            P.lk.resize(base + (size_t)S * 3, 1.0);
+            for (size_t k = 0; k < cm.matched.size(); k++) {
+                const sv field = col[9 + cm.matched[k]];
+                double *dst = &P.lk[base + (size_t)cm.unique[k] * 3];
+                if (n_miss > 0 && field.size() < 5) {
+                    dst[0] = dst[1] = dst[2] = 1.0;
+                    continue;
+                }
+                split(field, ':', sub);
+                if (sub.size() != fmt.size()) continue;
+                split(sub[ind_pl], ',', pl);
+                for (size_t j = 0; j < 3 && j < pl.size(); j++) dst[j] = std::pow(10.0, -std::fabs(to_double(pl[j])) / 10.0);
+            }
+            P.flags.push_back((uint8_t)((known ? FS_FLAG_KNOWN : 0) | (chrx ? FS_FLAG_CHRX : 0)));
+            P.items.push_back({VcfItem::Compute, line});
         }
-        batch.flags.push_back((uint8_t)((known ? FS_FLAG_KNOWN : 0) | (chrx ? FS_FLAG_CHRX : 0)));
-        items.push_back({VcfItem::Compute, line});
-        if (batch.count() >= kBatch || items.size() >= 4 * kBatch) {
-            g_stats.parse_s += now() - t_parse;
-            if (!(ok = flush())) break;
-            t_parse = now();
+    };
+
+    auto format_range = [&](Part &P) {
+        std::vector<sv> col, fmt;
+        std::string &o = P.out;
+        o.clear();
+        P.warn.clear();
+        P.failed = 0;
+        size_t v = P.first;
+        for (const VcfItem &it : P.items) {
+            split(it.line, '\t', col);
+            if (it.kind == VcfItem::Echo) { // first nine columns and the matched samples, each followed by a tab
+                for (int i = 0; i < 9; i++) {
+                    o.append(col[i]);
+                    o += '\t';
+                }
+                for (int m : cm.matched) {
+                    o.append(col[9 + m]);
+                    o += '\t';
+                }
+                o += '\n';
+                continue;
+            }
+            split(col[8], ':', fmt);
+            for (int i = 0; i < 8; i++) {
+                o.append(col[i]);
+                o += '\t';
+            }
+            o.append(col[8]);
+            o += ":GPP:FPP:FGT\t";
+            const bool failed = batch.status[v] != 0;
+            if (failed) { // file.cpp:607-619
+                P.warn += "Warning: this variant hasn't been calculated: \n";
+                P.warn.append(it.line);
+                P.warn += '\n';
+                P.failed++;
+            }
+            bool any_missing = false;
+            for (int m : cm.matched) any_missing |= col[9 + m].size() < 5;
+            for (size_t k = 0; k < cm.matched.size(); k++) {
+                const sv field = col[9 + cm.matched[k]];
+                if (failed) {
+                    o.append(field);
+                    o += ":NA:NA:NA\t";
+                    continue;
+                }
+                if (any_missing && field.size() < 5) { // file.cpp:927-933
+                    for (size_t j = 0; j < fmt.size(); j++) o += "NA:";
+                } else {
+                    o.append(field);
+                    o += ':';
+                }
+                const size_t off = (v * S + cm.unique[k]) * 3;
+                put_calls(o, &batch.single[off], &batch.post[off], batch.gt[v * S + cm.unique[k]]);
+            }
+            o += '\n';
+            v++;
         }
+    };
+
+    std::fwrite(out.data(), 1, out.size(), fout); // header
+    out.clear();
+    Lines in(data);
+    std::vector<sv> block;
+    bool eof = false;
+    while (!eof && ok) {
+        double t0 = now();
+        block.clear();
+        sv line;
+        while (block.size() < kBatch) {
+            if (!in.next(line) || line.size() < 2) { // the reference stops at the first line shorter than two characters
+                eof = true;
+                break;
+            }
+            if (line[0] == '#') continue;
+            block.push_back(line);
+        }
+        if (block.empty()) break;
+        g_stats.records += (long long)block.size();
+        run_parallel(n_threads, [&](int t) {
+            const size_t lo = block.size() * (size_t)t / n_threads, hi = block.size() * (size_t)(t + 1) / n_threads;
+            parse_range(parts[t], block.data() + lo, hi - lo);
+        });
+        size_t total = 0;
+        for (Part &P : parts) {
+            P.first = total;
+            total += P.flags.size();
+        }
+        batch.lk.resize(total * S * 3);
+        batch.flags.resize(total);
+        for (Part &P : parts) {
+            if (P.flags.empty()) continue;
+            std::memcpy(&batch.lk[P.first * S * 3], P.lk.data(), P.lk.size() * sizeof(double));
+            std::memcpy(&batch.flags[P.first], P.flags.data(), P.flags.size());
+        }
+        g_stats.parse_s += now() - t0;
+        if (total && !batch.run(eng, opt.method, S, burn, rep, opt.seed, v_offset)) {
+            ok = false;
+            break;
+        }
+        t0 = now();
+        run_parallel(n_threads, [&](int t) { format_range(parts[t]); });
+        for (Part &P : parts) {
+            std::fwrite(P.out.data(), 1, P.out.size(), fout);
+            if (!P.warn.empty()) std::cout << P.warn << std::flush;
+            g_stats.failed += P.failed;
+        }
+        v_offset += (long long)total;
+        g_stats.computed += (long long)total;
+        g_stats.write_s += now() - t0;
     }
-    g_stats.parse_s += now() - t_parse;
-    if (ok) ok = flush();
-    std::fwrite(out.data(), 1, out.size(), fout);
     std::fclose(fout);
     g_stats.total_s = now() - t_start;
     emit_stats();
@@ -634,80 +695,124 @@ bool run_lk(const LkOptions &opt, const PedRows &ped) {
         return false;
     }
 
-    std::vector<sv> lines, col, pl;
+    // blocks of up to kBatch rows; decoding and formatting are spread over host threads (see run_vcf)
+    struct Part {
+        std::vector<sv> lines;
+        std::vector<double> lk;
+        std::string out, warn;
+        long long failed = 0;
+        size_t first = 0;
+    };
+    const int n_threads = host_threads();
+    std::vector<Part> parts((size_t)n_threads);
     Pending batch;
     long long v_offset = 0;
     bool ok = true;
-    auto flush = [&]() -> bool {
-        // the LK driver calls the engine with Known = false, chrType = 0 (file.cpp:1751,1768,1785): flags stay 0
-        if (batch.count() && !batch.run(eng, opt.method, S, opt.num_burn_in, opt.num_rep, opt.seed, v_offset)) return false;
-        const double t0 = now();
-        for (size_t v = 0; v < lines.size(); v++) {
-            split(lines[v], '\t', col);
-            out += "LK:GPP:FPP:FGT\t";
+
+    auto parse_range = [&](Part &P, const sv *rows, size_t n) {
+        std::vector<sv> col, pl;
+        P.lines.clear();
+        P.lk.clear();
+        for (size_t li = 0; li < n; li++) {
+            split(rows[li], '\t', col);
+            if (col.size() < cm.ped_row.size()) continue; // malformed row: the reference would read out of bounds
+            const size_t base = P.lk.size();
+            P.lk.resize(base + (size_t)S * 3, 1.0);
+            for (size_t k = 0; k < cm.matched.size(); k++) {
+                double *dst = &P.lk[base + (size_t)cm.unique[k] * 3];
+                split(col[cm.matched[k]], ',', pl);
+                for (size_t j = 0; j < 3 && j < pl.size(); j++) {
+                    const double x = to_double(pl[j]);
+                    switch (opt.lk_type) { // file.cpp:1719-1738
+                    case 2: dst[j] = std::pow(10.0, x); break;
+                    case 3: dst[j] = std::exp(x); break;
+                    case 4: dst[j] = std::pow(10.0, -x / 10.0); break;
+                    default: dst[j] = x; break;
+                    }
+                }
+            }
+            P.lines.push_back(rows[li]);
+        }
+    };
+    auto format_range = [&](Part &P) {
+        std::vector<sv> col;
+        std::string &o = P.out;
+        o.clear();
+        P.warn.clear();
+        P.failed = 0;
+        size_t v = P.first;
+        for (const sv row : P.lines) {
+            split(row, '\t', col);
+            o += "LK:GPP:FPP:FGT\t";
             const bool failed = batch.status[v] != 0;
             if (failed) {
-                std::cout << "Warning: this variant hasn't been calculated: " << std::endl;
-                std::cout << lines[v] << std::endl;
-                g_stats.failed++;
+                P.warn += "Warning: this variant hasn't been calculated: \n";
+                P.warn.append(row);
+                P.warn += '\n';
+                P.failed++;
             }
             for (size_t k = 0; k < cm.matched.size(); k++) {
-                out.append(col[cm.matched[k]]);
+                o.append(col[cm.matched[k]]);
                 if (failed) {
-                    out += ":NA:NA:NA\t";
+                    o += ":NA:NA:NA\t";
                     continue;
                 }
-                out += ':';
-                const size_t o = (v * S + cm.unique[k]) * 3;
-                put_calls(out, &batch.single[o], &batch.post[o], batch.gt[v * S + cm.unique[k]]);
+                o += ':';
+                const size_t off = (v * S + cm.unique[k]) * 3;
+                put_calls(o, &batch.single[off], &batch.post[off], batch.gt[v * S + cm.unique[k]]);
             }
-            out += '\n';
-            if (out.size() > (1u << 23)) {
-                std::fwrite(out.data(), 1, out.size(), fout);
-                out.clear();
-            }
+            o += '\n';
+            v++;
         }
-        v_offset += (long long)batch.count();
-        g_stats.computed += (long long)batch.count();
-        lines.clear();
-        batch.clear();
-        g_stats.write_s += now() - t0;
-        return true;
     };
 
-    sv line;
-    double t_parse = now();
-    while (in.next(line)) {
-        if (line.size() < 2) break;
-        g_stats.records++;
-        split(line, '\t', col);
-        if (col.size() < cm.ped_row.size()) continue; // malformed row: the reference would read out of bounds
-        const size_t base = batch.lk.size();
-        batch.lk.resize(base + (size_t)S * 3, 1.0);
-        for (size_t k = 0; k < cm.matched.size(); k++) {
-            double *dst = &batch.lk[base + (size_t)cm.unique[k] * 3];
-            split(col[cm.matched[k]], ',', pl);
-            for (size_t j = 0; j < 3 && j < pl.size(); j++) {
-                const double x = to_double(pl[j]);
-                switch (opt.lk_type) { // file.cpp:1719-1738
-                case 2: dst[j] = std::pow(10.0, x); break;
-                case 3: dst[j] = std::exp(x); break;
-                case 4: dst[j] = std::pow(10.0, -x / 10.0); break;
-                default: dst[j] = x; break;
-                }
+    std::fwrite(out.data(), 1, out.size(), fout); // header
+    out.clear();
+    std::vector<sv> block;
+    bool eof = false;
+    while (!eof && ok) {
+        double t0 = now();
+        block.clear();
+        sv line;
+        while (block.size() < kBatch) {
+            if (!in.next(line) || line.size() < 2) {
+                eof = true;
+                break;
             }
+            block.push_back(line);
         }
-        batch.flags.push_back(0);
-        lines.push_back(line);
-        if (batch.count() >= kBatch) {
-            g_stats.parse_s += now() - t_parse;
-            if (!(ok = flush())) break;
-            t_parse = now();
+        if (block.empty()) break;
+        g_stats.records += (long long)block.size();
+        run_parallel(n_threads, [&](int t) {
+            const size_t lo = block.size() * (size_t)t / n_threads, hi = block.size() * (size_t)(t + 1) / n_threads;
+            parse_range(parts[t], block.data() + lo, hi - lo);
+        });
+        size_t total = 0;
+        for (Part &P : parts) {
+            P.first = total;
+            total += P.lines.size();
         }
+        // the LK driver calls the engine with Known = false, chrType = 0 (file.cpp:1751,1768,1785): flags stay 0
+        batch.lk.resize(total * S * 3);
+        batch.flags.assign(total, 0);
+        for (Part &P : parts)
+            if (!P.lines.empty()) std::memcpy(&batch.lk[P.first * S * 3], P.lk.data(), P.lk.size() * sizeof(double));
+        g_stats.parse_s += now() - t0;
+        if (total && !batch.run(eng, opt.method, S, opt.num_burn_in, opt.num_rep, opt.seed, v_offset)) {
+            ok = false;
+            break;
+        }
+        t0 = now();
+        run_parallel(n_threads, [&](int t) { format_range(parts[t]); });
+        for (Part &P : parts) {
+            std::fwrite(P.out.data(), 1, P.out.size(), fout);
+            if (!P.warn.empty()) std::cout << P.warn << std::flush;
+            g_stats.failed += P.failed;
+        }
+        v_offset += (long long)total;
+        g_stats.computed += (long long)total;
+        g_stats.write_s += now() - t0;
     }
-    g_stats.parse_s += now() - t_parse;
-    if (ok) ok = flush();
-    std::fwrite(out.data(), 1, out.size(), fout);
     std::fclose(fout);
     g_stats.total_s = now() - t_start;
     emit_stats();
