@@ -380,7 +380,8 @@ def main():
     traffic = None
     prof = os.path.join(ROOT, "profiles", "es_trio_traffic.json")
     if os.path.exists(prof):
-        traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+        # dram__bytes_read + dram__bytes_write of one `ncu --set full` capture, scaled to this launch's variant count
+        traffic = json.load(open(prof)).get("dram_bytes_per_variant", 0.0) * args.variants or None
     out.update({
         "metric": "variants/sec (ES peeling, trio)", "value": value, "unit": "variants/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -35,6 +35,15 @@ template <int X, int U> struct BnBlock {
                                                  const int (&stride)[BN_MAX_UNROLL][BN_MAX_UNROLL],
                                                  const int (&off)[U], double prefix, double (&acc)[U][3]) {
         const double2 f01 = *reinterpret_cast<const double2 *>(tab + off[X]);
+        if constexpr (X == U - 1) {
+            // innermost level: each joint prefix*f[d] is formed inside the FMA that adds it to the member's bin; the
+            // sum of the three joints is prefix * (f0+f1+f2), the row sum being tabulated next to the row
+            const double2 f2s = *reinterpret_cast<const double2 *>(tab + off[X] + 2);
+            acc[X][0] = fma(prefix, f01.x, acc[X][0]);
+            acc[X][1] = fma(prefix, f01.y, acc[X][1]);
+            acc[X][2] = fma(prefix, f2s.x, acc[X][2]);
+            return prefix * f2s.y;
+        }
         const double f2 = tab[off[X] + 2];
         double total = 0.0;
 #pragma unroll
@@ -56,7 +65,34 @@ template <int X, int U> struct BnBlock {
     }
 };
 
-template <int U>
+// The same enumeration when no unrolled level is the parent of another one (host/bn_plan.cpp puts childless
+// members innermost, so this is the common case): the U factor vectors depend on outer digits only, are loaded
+// once per block and the whole 3^U nest runs out of registers.
+template <int X, int U> struct BnBlockRegs {
+    static __device__ __forceinline__ double run(const double (&f)[U][4], double prefix, double (&acc)[U][3]) {
+        if constexpr (X == U - 1) { // see BnBlock: joints formed inside the FMAs, their sum is prefix * row sum
+            acc[X][0] = fma(prefix, f[X][0], acc[X][0]);
+            acc[X][1] = fma(prefix, f[X][1], acc[X][1]);
+            acc[X][2] = fma(prefix, f[X][2], acc[X][2]);
+            return prefix * f[X][3];
+        }
+        double total = 0.0;
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+            const double joint = prefix * f[X][d];
+            double below;
+            if constexpr (X == U - 1)
+                below = joint;
+            else
+                below = BnBlockRegs<X + 1, U>::run(f, joint, acc);
+            acc[X][d] += below;
+            total = (d == 0) ? below : total + below;
+        }
+        return total;
+    }
+};
+
+template <int U, bool INDEP>
 __global__ void __launch_bounds__(256) bn_kernel(const __grid_constant__ BnParams P, const BatchPtrs B, int n_tiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const RunConstants &C = P.C;
@@ -109,19 +145,23 @@ __global__ void __launch_bounds__(256) bn_kernel(const __grid_constant__ BnParam
             s_state[slot] = failed ? 2 : (pedigree_needed ? 0 : 1);
         }
         // ---- per-variant factor tables ---------------------------------------------------------------
-        if (live) {
+        if (live) { // one table row (3 factors and their sum) per thread
             double *tab = s_tab + slot * TD;
-            for (int L = 0; L < N; L++) {
+            const int n_rows = TD >> 2;
+            for (int q = code; q < n_rows; q += G) {
+                const int L = pl.row_level[q], row = q - (pl.tab_off[L] >> 2);
                 const bool founder = pl.founder[L] != 0, male = pl.male[L] != 0;
                 const int col = pl.col[L];
                 const int kind = chrx ? (male ? K_TAB_XM : K_TAB_XF) : K_TAB_AUTO;
-                const int n_entries = founder ? 3 : 27;
-                for (int e = code; e < n_entries; e += G) {
-                    const int row = e / 3, g = e - 3 * row;
+                double f[3];
+#pragma unroll
+                for (int g = 0; g < 3; g++) {
                     const double lk = col >= 0 ? lkv[col * 3 + g] : 1.0;
-                    const double base = founder ? (male ? pick3(pr.m, g) : pick3(pr.a, g)) : C.tab[kind][g * 9 + row];
-                    tab[pl.tab_off[L] + row * 4 + g] = __dmul_rn(base, lk);
+                    const double base = founder ? (male ? pr.m[g] : pr.a[g]) : C.tab[kind][g * 9 + row];
+                    f[g] = __dmul_rn(base, lk); // the reference's indProb (family.cpp:899-909)
                 }
+                *reinterpret_cast<double2 *>(tab + 4 * q) = make_double2(f[0], f[1]);
+                *reinterpret_cast<double2 *>(tab + 4 * q + 2) = make_double2(f[2], __dadd_rn(__dadd_rn(f[0], f[1]), f[2]));
             }
         }
         __syncthreads();
@@ -161,7 +201,22 @@ __global__ void __launch_bounds__(256) bn_kernel(const __grid_constant__ BnParam
                     const int L = first_unrolled + x;
                     off[x] = pl.tab_off[L] + 4 * bn_row(cfg, pl.sh_m[L], pl.sh_f[L]);
                 }
-                const double block_total = BnBlock<0, U>::run(tab, pl.ustride, off, prefix, acc);
+                double block_total;
+                if constexpr (INDEP) {
+                    double f[U][4];
+#pragma unroll
+                    for (int x = 0; x < U; x++) {
+                        const double2 f01 = *reinterpret_cast<const double2 *>(tab + off[x]);
+                        const double2 f2s = *reinterpret_cast<const double2 *>(tab + off[x] + 2);
+                        f[x][0] = f01.x;
+                        f[x][1] = f01.y;
+                        f[x][2] = f2s.x;
+                        f[x][3] = f2s.y;
+                    }
+                    block_total = BnBlockRegs<0, U>::run(f, prefix, acc);
+                } else {
+                    block_total = BnBlock<0, U>::run(tab, pl.ustride, off, prefix, acc);
+                }
                 thread_total += block_total;
                 if (R == 0) break;
                 // marginal bins of the rolled levels, then advance the odometer (innermost rolled level fastest)
@@ -285,28 +340,30 @@ size_t bn_smem_bytes(const BnParams &P) {
     return ((d * sizeof(double) + pl.vpb) + 15) & ~(size_t)15;
 }
 
-template <int U> static cudaError_t launch_bn_u(const BnParams &P, const BatchPtrs &B, int sm_count, cudaStream_t stream) {
+template <int U, bool INDEP>
+static cudaError_t launch_bn_u(const BnParams &P, const BatchPtrs &B, int sm_count, cudaStream_t stream) {
     const size_t smem = bn_smem_bytes(P);
-    cudaError_t rc = cudaFuncSetAttribute(bn_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t rc = cudaFuncSetAttribute(bn_kernel<U, INDEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) return rc;
     int per_sm = 0;
-    rc = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_kernel<U>, P.plan.threads, smem);
+    rc = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bn_kernel<U, INDEP>, P.plan.threads, smem);
     if (rc != cudaSuccess) return rc;
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
     const int64_t n_tiles = (B.V + P.plan.vpb - 1) / P.plan.vpb;
     if (n_tiles > 0x7fffffff) return cudaErrorInvalidValue;
     const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)sm_count * per_sm);
-    bn_kernel<U><<<grid, P.plan.threads, smem, stream>>>(P, B, (int)n_tiles);
+    bn_kernel<U, INDEP><<<grid, P.plan.threads, smem, stream>>>(P, B, (int)n_tiles);
     return cudaGetLastError();
 }
 
 cudaError_t launch_bn(const BnParams &P, const BatchPtrs &B, int sm_count, cudaStream_t stream) {
     if (B.V <= 0) return cudaSuccess;
+    const bool indep = P.plan.independent != 0;
     switch (P.plan.u) {
-    case 1: return launch_bn_u<1>(P, B, sm_count, stream);
-    case 2: return launch_bn_u<2>(P, B, sm_count, stream);
-    case 3: return launch_bn_u<3>(P, B, sm_count, stream);
-    case 4: return launch_bn_u<4>(P, B, sm_count, stream);
+    case 1: return launch_bn_u<1, false>(P, B, sm_count, stream);
+    case 2: return indep ? launch_bn_u<2, true>(P, B, sm_count, stream) : launch_bn_u<2, false>(P, B, sm_count, stream);
+    case 3: return indep ? launch_bn_u<3, true>(P, B, sm_count, stream) : launch_bn_u<3, false>(P, B, sm_count, stream);
+    case 4: return indep ? launch_bn_u<4, true>(P, B, sm_count, stream) : launch_bn_u<4, false>(P, B, sm_count, stream);
     default: return cudaErrorInvalidValue;
     }
 }

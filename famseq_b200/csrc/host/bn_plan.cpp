@@ -70,6 +70,7 @@ int build_bn_plan(const Pedigree &ped, BnPlan &out, std::string &err) {
             p.sh_f[L] = (uint8_t)(2 * level_of[ped.father[i]]);
         }
         p.tab_off[L] = off;
+        for (int q = 0; q < (ped.founder(i) ? 1 : 9); q++) p.row_level[off / 4 + q] = (uint8_t)L;
         off += ped.founder(i) ? 4 : 36;
     }
     p.table_doubles = off;
@@ -83,6 +84,12 @@ int build_bn_plan(const Pedigree &ped, BnPlan &out, std::string &err) {
             if (ped.father[i] == j) p.ustride[x][y] = 4;
         }
     }
+    p.independent = 1;
+    for (int x = 0; x < p.u; x++)
+        for (int y = 0; y < x; y++)
+            if (p.ustride[x][y]) p.independent = 0;
+    if (const char *env = std::getenv("FAMSEQ_BN_GENERIC")) // tuning / test knob: force the general unrolled block
+        if (env[0] == '1') p.independent = 0;
     out = p;
     return FS_OK;
 }

@@ -34,9 +34,13 @@ struct BnPlan {
     uint8_t founder[32];
     uint8_t sh_m[32], sh_f[32]; // bit position in the packed configuration word of the mother's / father's digit
     int32_t tab_off[32];        // offset (doubles) of the level's table inside the variant's table block
+    uint8_t row_level[288];     // level that owns table row q (row q starts at double 4q)
     // unrolled level x (0 = outermost unrolled): row stride (in doubles: 0, 4 or 12) contributed by the
     // digit of unrolled level y < x when y is its father / mother
     int32_t ustride[BN_MAX_UNROLL][BN_MAX_UNROLL];
+    // 1 when no unrolled level is a parent of another unrolled level (all ustride are zero): the factor vectors of
+    // the unrolled block then depend on outer digits only and are loaded once per block instead of once per use
+    int32_t independent = 0;
 };
 
 } // namespace famseq
