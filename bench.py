@@ -311,7 +311,8 @@ def main():
     ap.add_argument("--variants", type=int, default=10_000_000, help="ES trio variants per GPU")
     ap.add_argument("--bn-variants", type=int, default=1_000_000)
     ap.add_argument("--mcmc-variants", type=int, default=1_000_000)
-    ap.add_argument("--methods", default="es,bn,mcmc", help="which method lines to time (es is the headline)")
+    ap.add_argument("--es14-variants", type=int, default=1_000_000)
+    ap.add_argument("--methods", default="es,es14,bn,mcmc", help="which method lines to time (es is the headline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -397,6 +398,19 @@ def main():
 
     # ---- the other two methods ---------------------------------------------------------------------------
     sub = {}
+    if "es14" in methods:  # the general message-program interpreter (any loop-free pedigree), HBM roofline
+        wl = Workload("es14", ped14, "es", args.es14_variants)
+        with engine(ped14) as eng:
+            ms_e, l_e, clk_e, failed_e, keep = time_device_path(torch, dist, fs, eng, wl, rank, world, 5, 2, local_rank)
+        del keep
+        torch.cuda.empty_cache()
+        ach = algorithmic_bytes(14) * args.es14_variants / (ms_e * 1e-3) / 1e9
+        sub["ES_ped14"] = {"workload": "synthetic 14-member 3-generation pedigree, ES peeling through the message-program interpreter",
+                           "variants_per_gpu": args.es14_variants, "value": world * args.es14_variants / (ms_e * 1e-3),
+                           "unit": "variants/s", "ms_per_step": ms_e, "steps": 5, "warmup": 2, "gpu_launches": l_e, "clocks": clk_e,
+                           "failed_variants": failed_e,
+                           "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                                        "algorithmic_bytes_per_variant": algorithmic_bytes(14), "kernel": "es_kernel<TB>"}}
     if "bn" in methods:
         N = 14
         wl = Workload("bn", ped14, "bn", args.bn_variants)

@@ -69,31 +69,31 @@ template <int X, int U> struct BnBlock {
 // members innermost, so this is the common case): the U factor vectors depend on outer digits only, are loaded
 // once per block and the whole 3^U nest runs out of registers.
 template <int X, int U> struct BnBlockRegs {
-    static __device__ __forceinline__ double run(const double (&f)[U][4], double prefix, double (&acc)[U][3]) {
+    // `inner` are the bins of the innermost level, one set per digit of the level above it: three times shorter
+    // dependent FMA chains than a single set (they are summed once, after the enumeration)
+    static __device__ __forceinline__ double run(const double (&f)[U][4], double prefix, double (&acc)[U][3],
+                                                 double (&inner)[3][3], int above) {
         if constexpr (X == U - 1) { // see BnBlock: joints formed inside the FMAs, their sum is prefix * row sum
-            acc[X][0] = fma(prefix, f[X][0], acc[X][0]);
-            acc[X][1] = fma(prefix, f[X][1], acc[X][1]);
-            acc[X][2] = fma(prefix, f[X][2], acc[X][2]);
+            inner[above][0] = fma(prefix, f[X][0], inner[above][0]);
+            inner[above][1] = fma(prefix, f[X][1], inner[above][1]);
+            inner[above][2] = fma(prefix, f[X][2], inner[above][2]);
             return prefix * f[X][3];
-        }
-        double total = 0.0;
+        } else {
+            double total = 0.0;
 #pragma unroll
-        for (int d = 0; d < 3; d++) {
-            const double joint = prefix * f[X][d];
-            double below;
-            if constexpr (X == U - 1)
-                below = joint;
-            else
-                below = BnBlockRegs<X + 1, U>::run(f, joint, acc);
-            acc[X][d] += below;
-            total = (d == 0) ? below : total + below;
+            for (int d = 0; d < 3; d++) {
+                const double joint = prefix * f[X][d];
+                const double below = BnBlockRegs<X + 1, U>::run(f, joint, acc, inner, d);
+                acc[X][d] += below;
+                total = (d == 0) ? below : total + below;
+            }
+            return total;
         }
-        return total;
     }
 };
 
 template <int U, bool INDEP>
-__global__ void __launch_bounds__(256) bn_kernel(const __grid_constant__ BnParams P, const BatchPtrs B, int n_tiles) {
+__global__ void __launch_bounds__(256, 2) bn_kernel(const __grid_constant__ BnParams P, const BatchPtrs B, int n_tiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const RunConstants &C = P.C;
     const BnPlan &pl = P.plan;
@@ -102,8 +102,8 @@ __global__ void __launch_bounds__(256) bn_kernel(const __grid_constant__ BnParam
     const int nthreads = blockDim.x;
     double *s_tab = reinterpret_cast<double *>(smem_raw);  // [VPB][TD] factor tables, rows of 4 doubles
     double *s_bins = s_tab + VPB * TD;                      // [VPB][N][3] marginal sums
-    double *s_priv = s_bins + VPB * N * 3;                  // [R][4][nthreads]: prefix, bins of a rolled level
-    double *s_red = s_priv + R * 4 * nthreads;              // [3U+1][nthreads]: unrolled bins, thread total
+    double *s_priv = s_bins + VPB * N * 3;                  // [R][5][nthreads]: prefix, 3 bins, pending mass of a rolled level
+    double *s_red = s_priv + R * 5 * nthreads;              // [3U+1][nthreads]: unrolled bins, thread total
     double *s_single = s_red + (3 * U + 1) * nthreads;      // [VPB][S][3]
     uint8_t *s_state = reinterpret_cast<uint8_t *>(s_single + VPB * S * 3); // [VPB] 0 enumerate, 1 single, 2 failed
 
@@ -171,6 +171,9 @@ __global__ void __launch_bounds__(256) bn_kernel(const __grid_constant__ BnParam
 #pragma unroll
         for (int x = 0; x < U; x++) acc[x][0] = acc[x][1] = acc[x][2] = 0.0;
         double thread_total = 0.0;
+        double inner[3][3]; // INDEP only: split bins of the innermost level
+#pragma unroll
+        for (int k = 0; k < 3; k++) inner[k][0] = inner[k][1] = inner[k][2] = 0.0;
         if (live && s_state[slot] == 0) {
             const double *tab = s_tab + slot * TD;
             uint64_t cfg = 0;
@@ -186,68 +189,84 @@ __global__ void __launch_bounds__(256) bn_kernel(const __grid_constant__ BnParam
             for (int j = 0; j < H; j++)
                 prefix *= tab[pl.tab_off[j] + 4 * bn_row(cfg, pl.sh_m[j], pl.sh_f[j]) + (int)((cfg >> (2 * j)) & 3u)];
             const double spread_prefix = prefix;
-            // rolled levels start at digit 0
+            // rolled levels start at digit 0; private state per rolled level: prefix, 3 bins, pending mass
             for (int q = 0; q < R; q++) {
                 const int L = H + q;
                 prefix *= tab[pl.tab_off[L] + 4 * bn_row(cfg, pl.sh_m[L], pl.sh_f[L])];
-                double *pv = s_priv + (q * 4) * nthreads + tid;
+                double *pv = s_priv + (q * 5) * nthreads + tid;
                 pv[0] = prefix;
-                pv[nthreads] = pv[2 * nthreads] = pv[3 * nthreads] = 0.0;
+                pv[nthreads] = pv[2 * nthreads] = pv[3 * nthreads] = pv[4 * nthreads] = 0.0;
             }
+            int off[U];
+            double f[INDEP ? U : 1][4];
+            bool reload = true; // the unrolled levels' table rows depend on outer digits only
             for (;;) {
-                int off[U];
-#pragma unroll
-                for (int x = 0; x < U; x++) {
-                    const int L = first_unrolled + x;
-                    off[x] = pl.tab_off[L] + 4 * bn_row(cfg, pl.sh_m[L], pl.sh_f[L]);
-                }
-                double block_total;
-                if constexpr (INDEP) {
-                    double f[U][4];
+                if (reload) {
 #pragma unroll
                     for (int x = 0; x < U; x++) {
-                        const double2 f01 = *reinterpret_cast<const double2 *>(tab + off[x]);
-                        const double2 f2s = *reinterpret_cast<const double2 *>(tab + off[x] + 2);
-                        f[x][0] = f01.x;
-                        f[x][1] = f01.y;
-                        f[x][2] = f2s.x;
-                        f[x][3] = f2s.y;
+                        const int L = first_unrolled + x;
+                        off[x] = pl.tab_off[L] + 4 * bn_row(cfg, pl.sh_m[L], pl.sh_f[L]);
                     }
-                    block_total = BnBlockRegs<0, U>::run(f, prefix, acc);
-                } else {
-                    block_total = BnBlock<0, U>::run(tab, pl.ustride, off, prefix, acc);
-                }
-                thread_total += block_total;
-                if (R == 0) break;
-                // marginal bins of the rolled levels, then advance the odometer (innermost rolled level fastest)
-                int q = R - 1;
-                bool carry = true;
-                for (int k = R - 1; k >= 0; k--) {
-                    const int L = H + k;
-                    const int d = (int)((cfg >> (2 * L)) & 3u);
-                    s_priv[(k * 4 + 1 + d) * nthreads + tid] += block_total;
-                    if (carry) {
-                        if (d == 2) {
-                            cfg &= ~(3ull << (2 * L));
-                        } else {
-                            cfg += 1ull << (2 * L);
-                            carry = false;
-                            q = k;
+                    if constexpr (INDEP) {
+#pragma unroll
+                        for (int x = 0; x < U; x++) {
+                            const double2 f01 = *reinterpret_cast<const double2 *>(tab + off[x]);
+                            const double2 f2s = *reinterpret_cast<const double2 *>(tab + off[x] + 2);
+                            f[x][0] = f01.x;
+                            f[x][1] = f01.y;
+                            f[x][2] = f2s.x;
+                            f[x][3] = f2s.y;
                         }
                     }
                 }
-                if (carry) break; // every rolled digit wrapped: done
-                // levels q .. R-1 changed: rebuild their prefixes
-                prefix = (q == 0) ? spread_prefix : s_priv[((q - 1) * 4) * nthreads + tid];
-                for (int k = q; k < R; k++) {
+                double block_total;
+                if constexpr (INDEP)
+                    block_total = BnBlockRegs<0, U>::run(f, prefix, acc, inner, 0);
+                else
+                    block_total = BnBlock<0, U>::run(tab, pl.ustride, off, prefix, acc);
+                thread_total += block_total;
+                if (R == 0) break;
+                // Advance the odometer (innermost rolled level fastest) and book the block's mass into the bins of the
+                // rolled levels hierarchically: a level's bin is touched only when its digit changes; what was
+                // accumulated under an unchanged digit waits in the level's `pending` slot.
+                double mass = block_total;
+                int k = R - 1;
+                bool finished = false;
+                for (;;) {
                     const int L = H + k;
-                    prefix *= tab[pl.tab_off[L] + 4 * bn_row(cfg, pl.sh_m[L], pl.sh_f[L]) + (int)((cfg >> (2 * L)) & 3u)];
-                    s_priv[(k * 4) * nthreads + tid] = prefix;
+                    const int d = (int)((cfg >> (2 * L)) & 3u);
+                    s_priv[(k * 5 + 1 + d) * nthreads + tid] += mass;
+                    if (d < 2) {
+                        cfg += 1ull << (2 * L);
+                        if (k > 0) s_priv[((k - 1) * 5 + 4) * nthreads + tid] += mass;
+                        break;
+                    }
+                    cfg &= ~(3ull << (2 * L));
+                    if (k == 0) {
+                        finished = true;
+                        break;
+                    }
+                    k--;
+                    mass += s_priv[(k * 5 + 4) * nthreads + tid];
+                    s_priv[(k * 5 + 4) * nthreads + tid] = 0.0;
                 }
+                if (finished) break; // every rolled digit wrapped: done
+                // levels k .. R-1 changed: rebuild their prefixes
+                prefix = (k == 0) ? spread_prefix : s_priv[((k - 1) * 5) * nthreads + tid];
+                for (int j = k; j < R; j++) {
+                    const int L = H + j;
+                    prefix *= tab[pl.tab_off[L] + 4 * bn_row(cfg, pl.sh_m[L], pl.sh_f[L]) + (int)((cfg >> (2 * L)) & 3u)];
+                    s_priv[(j * 5) * nthreads + tid] = prefix;
+                }
+                reload = k <= pl.unrolled_dep;
             }
         } else {
             for (int q = 0; q < R; q++)
-                for (int k = 1; k < 4; k++) s_priv[(q * 4 + k) * nthreads + tid] = 0.0;
+                for (int k = 1; k < 4; k++) s_priv[(q * 5 + k) * nthreads + tid] = 0.0;
+        }
+        if constexpr (INDEP) {
+#pragma unroll
+            for (int g = 0; g < 3; g++) acc[U - 1][g] = (inner[0][g] + inner[1][g]) + inner[2][g];
         }
 #pragma unroll
         for (int x = 0; x < U; x++)
@@ -268,7 +287,7 @@ __global__ void __launch_bounds__(256) bn_kernel(const __grid_constant__ BnParam
                     for (int j = 0; j < L; j++) cc /= 3;
                     return (cc % 3 == g) ? s_red[(3 * U) * nthreads + t] : 0.0;
                 }
-                if (L < H + R) return s_priv[((L - H) * 4 + 1 + g) * nthreads + t];
+                if (L < H + R) return s_priv[((L - H) * 5 + 1 + g) * nthreads + t];
                 return s_red[((L - first_unrolled) * 3 + g) * nthreads + t];
             };
             if (G >= 32) {
@@ -335,7 +354,7 @@ __global__ void __launch_bounds__(256) bn_kernel(const __grid_constant__ BnParam
 
 size_t bn_smem_bytes(const BnParams &P) {
     const BnPlan &pl = P.plan;
-    size_t d = (size_t)pl.vpb * pl.table_doubles + (size_t)pl.vpb * pl.n_levels * 3 + (size_t)pl.r * 4 * pl.threads +
+    size_t d = (size_t)pl.vpb * pl.table_doubles + (size_t)pl.vpb * pl.n_levels * 3 + (size_t)pl.r * 5 * pl.threads +
                (size_t)(3 * pl.u + 1) * pl.threads + (size_t)pl.vpb * P.C.s * 3;
     return ((d * sizeof(double) + pl.vpb) + 15) & ~(size_t)15;
 }

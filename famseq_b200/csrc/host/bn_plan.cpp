@@ -84,6 +84,15 @@ int build_bn_plan(const Pedigree &ped, BnPlan &out, std::string &err) {
             if (ped.father[i] == j) p.ustride[x][y] = 4;
         }
     }
+    p.unrolled_dep = -1;
+    for (int x = 0; x < p.u; x++) {
+        const int i = order[first_unrolled + x];
+        if (ped.founder(i)) continue;
+        for (int par : {ped.mother[i], ped.father[i]}) {
+            const int q = level_of[par] - p.h; // rolled index of the parent, if it is a rolled level
+            if (q >= 0 && q < p.r && q > p.unrolled_dep) p.unrolled_dep = q;
+        }
+    }
     p.independent = 1;
     for (int x = 0; x < p.u; x++)
         for (int y = 0; y < x; y++)
