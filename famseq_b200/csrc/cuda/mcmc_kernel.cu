@@ -34,7 +34,15 @@ namespace famseq {
 
 namespace {
 
-constexpr int kCopies = 16; // replicas of every table entry
+constexpr int kCopies = 16;      // replicas of every table entry
+constexpr int kEntries = 81 + 27; // 3 x 27 transmission entries followed by 27 ones
+constexpr int kOnes = 81;
+
+__device__ __forceinline__ double lds64(uint32_t shared_addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(shared_addr));
+    return v;
+}
 
 __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
                                               uint32_t &o0, uint32_t &o1, uint32_t &o2, uint32_t &o3) {
@@ -71,15 +79,14 @@ struct Genotypes {
 
 // 1/s to ~1 ulp: hardware seed (MUFU.RCP64H) + two Newton steps; outside the safe range the IEEE divide.
 __device__ __forceinline__ double fast_reciprocal(double s) {
-    if (s > 1e-290 && s < 1e290) {
-        double x;
-        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(s));
-        double e = fma(-s, x, 1.0);
-        x = fma(x, e, x);
-        e = fma(-s, x, 1.0);
-        return fma(x, e, x);
-    }
-    return 1.0 / s;
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(s));
+    double e = fma(-s, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-s, x, 1.0);
+    x = fma(x, e, x);
+    if (!(s > 1e-290 && s < 1e290)) x = 1.0 / s; // rare
+    return x;
 }
 
 template <int TB>
@@ -89,13 +96,17 @@ __global__ void __launch_bounds__(TB) mcmc_kernel(const __grid_constant__ McmcPa
     const RunConstants &C = P.C;
     const McmcPlan &pl = P.plan;
     const int N = pl.n, S = C.s;
-    double *s_tab = reinterpret_cast<double *>(smem_raw); // [81][16]
-    double *s_w = s_tab + 81 * kCopies;                    // [N][3][TB] own factor: (1e6*prior)*lk or 1e6*lk
+    double *s_tab = reinterpret_cast<double *>(smem_raw); // [108][16]
+    double *s_w = s_tab + kEntries * kCopies;              // [N][3][TB] own factor: (1e6*prior)*lk or 1e6*lk
 
     const int tid = threadIdx.x, lane = tid & 31;
-    for (int e = tid; e < 81 * kCopies; e += TB) s_tab[e] = C.tab[(e / kCopies) / 27][(e / kCopies) % 27];
+    for (int e = tid; e < kEntries * kCopies; e += TB) {
+        const int entry = e / kCopies;
+        s_tab[e] = entry < 81 ? C.tab[entry / 27][entry % 27] : 1.0;
+    }
     __syncthreads();
-    const double *tab = s_tab + (lane & (kCopies - 1));
+    const uint32_t tab_addr = (uint32_t)__cvta_generic_to_shared(s_tab) + (uint32_t)(lane & (kCopies - 1)) * 8u;
+    const uint32_t w_addr = (uint32_t)__cvta_generic_to_shared(s_w) + (uint32_t)tid * 8u;
     double *w = s_w + tid;
     double *acc = scratch + (size_t)blockIdx.x * ((size_t)N * 3 * TB) + tid; // [member][g][TB], private to this thread
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
@@ -174,37 +185,57 @@ __global__ void __launch_bounds__(TB) mcmc_kernel(const __grid_constant__ McmcPa
         }
 
         // ---- sweeps ---------------------------------------------------------------------------------------------
+        // The step is written branch-light: founders and missing children multiply by a row of ones, the first two
+        // children are handled in line, shared memory is addressed with 32-bit shared-window addresses.
+        asm volatile("" ::: "memory");
         const int total_sweeps = burn + rep;
         for (int sweep = 1; sweep <= total_sweeps; sweep++) {
             const bool sampling = sweep > burn;
             for (int i = 0; i < N; i++) {
                 const uint32_t d = pl.member[i];
-                const bool male = (d >> 13) & 1u;
-                double w0 = w[(i * 3) * TB], w1 = w[(i * 3 + 1) * TB], w2 = w[(i * 3 + 2) * TB];
-                if (!((d >> 12) & 1u)) { // not a founder: transmission from the parents' current genotypes
-                    const int kind = chrx ? (male ? K_TAB_XM : K_TAB_XF) : K_TAB_AUTO;
-                    const double *t = tab + (kind * 27 + cur.get(d & 63u) * 3 + cur.get((d >> 6) & 63u)) * kCopies;
-                    w0 *= t[0];
-                    w1 *= t[9 * kCopies];
-                    w2 *= t[18 * kCopies];
+                const bool male = (d >> 13) & 1u, founder = (d >> 12) & 1u;
+                const uint32_t wa = w_addr + (uint32_t)i * (3u * TB * 8u);
+                double w0 = lds64(wa), w1 = lds64(wa + TB * 8), w2 = lds64(wa + 2 * TB * 8);
+                const int xkind = male ? 2 * 27 : 27; // chrX table of this member / of a child, by sex
+                {   // own factor: transmission from the parents' current genotypes (a row of ones for founders)
+                    const int row = cur.get(d & 63u) * 3 + cur.get((d >> 6) & 63u);
+                    const int e = founder ? kOnes : (chrx ? xkind : 0) + row;
+                    const uint32_t ta = tab_addr + (uint32_t)e * (kCopies * 8u);
+                    w0 *= lds64(ta);
+                    w1 *= lds64(ta + 9 * kCopies * 8);
+                    w2 *= lds64(ta + 18 * kCopies * 8);
                 }
-                if (!chrx || male) { // chrX: only males get the children factor (reference quirk)
-                    const int lb = (d >> 14) & 0xffu, le = lb + ((d >> 22) & 0xffu);
-                    const int step = male ? kCopies : 3 * kCopies; // this member sits in the father slot when male
-                    for (int k = lb; k < le; k++) {
-                        const uint32_t l = pl.link[k];
-                        const int kind = chrx ? (((l >> 12) & 1u) ? K_TAB_XM : K_TAB_XF) : K_TAB_AUTO;
-                        const int other = cur.get((l >> 6) & 63u);
-                        const double *t = tab + (kind * 27 + cur.get(l & 63u) * 9 + (male ? other * 3 : other)) * kCopies;
-                        w0 *= t[0];
-                        w1 *= t[step];
-                        w2 *= t[2 * step];
-                    }
+                const int lb = (d >> 14) & 0xffu;
+                const int n_links = (!chrx || male) ? (int)((d >> 22) & 0xffu) : 0; // chrX: only males get the children factor
+                const uint32_t step = male ? kCopies * 8u : 3u * kCopies * 8u;     // this member sits in the father slot when male
+                auto child_entry = [&](int k) -> int {
+                    const uint32_t l = pl.link[k];
+                    const int kind = chrx ? (((l >> 12) & 1u) ? 2 * 27 : 27) : 0;
+                    const int other = cur.get((l >> 6) & 63u);
+                    return kind + cur.get(l & 63u) * 9 + (male ? other * 3 : other);
+                };
+                {   // first two children in line (a row of ones when there are fewer)
+                    const int e0 = n_links > 0 ? child_entry(lb) : kOnes;
+                    const int e1 = n_links > 1 ? child_entry(lb + 1) : kOnes;
+                    const uint32_t a0 = tab_addr + (uint32_t)e0 * (kCopies * 8u), a1 = tab_addr + (uint32_t)e1 * (kCopies * 8u);
+                    const double x0 = lds64(a0), x1 = lds64(a0 + step), x2 = lds64(a0 + 2 * step);
+                    const double y0 = lds64(a1), y1 = lds64(a1 + step), y2 = lds64(a1 + 2 * step);
+                    w0 = (w0 * x0) * y0;
+                    w1 = (w1 * x1) * y1;
+                    w2 = (w2 * x2) * y2;
+                }
+                for (int k = lb + 2; k < lb + n_links; k++) { // third and later children
+                    const uint32_t a0 = tab_addr + (uint32_t)child_entry(k) * (kCopies * 8u);
+                    w0 *= lds64(a0);
+                    w1 *= lds64(a0 + step);
+                    w2 *= lds64(a0 + 2 * step);
                 }
                 const double sum = (w0 + w1) + w2;
                 if ((i & 3) == 0) philox4x32_10((uint32_t)sweep, (uint32_t)(i >> 2), gv_lo, gv_hi, k0, k1, r0, r1, r2, r3);
-                const int q = i & 3;
-                const uint32_t u = q == 0 ? r0 : (q == 1 ? r1 : (q == 2 ? r2 : r3));
+                const uint32_t u = r0; // words are consumed in order: rotate the block
+                r0 = r1;
+                r1 = r2;
+                r2 = r3;
                 const double rd = ((double)u + 0.5) * (1.0 / 4294967296.0);
                 // rd < w0/sum and rd > 1 - w2/sum decided without the division; a non-positive sum means all-zero
                 // weights in the reference, which then draws genotype 1 (family.cpp:2142-2173)
@@ -212,8 +243,8 @@ __global__ void __launch_bounds__(TB) mcmc_kernel(const __grid_constant__ McmcPa
                 int g = (thr < w0) ? 0 : ((thr > sum - w2) ? 2 : 1);
                 if (!(sum > 0.0)) g = 1;
                 cur.set(i, g);
-                if (sampling && sum > 0.0) { // family.cpp:2175-2178, Rao-Blackwellised
-                    const double inv = fast_reciprocal(sum);
+                if (sampling) { // family.cpp:2175-2178, Rao-Blackwellised; all-zero weights add nothing
+                    const double inv = sum > 0.0 ? fast_reciprocal(sum) : 0.0;
                     double *a = acc + (size_t)((i * 3) * TB);
                     atomicAdd(a, w0 * inv);
                     atomicAdd(a + TB, w1 * inv);
@@ -268,7 +299,7 @@ template <int TB> cudaError_t launch_tb(const McmcParams &P, const BatchPtrs &B,
 
 } // namespace
 
-size_t mcmc_smem_bytes(const McmcParams &P, int tb) { return (size_t)(81 * kCopies + P.plan.n * 3 * tb) * sizeof(double); }
+size_t mcmc_smem_bytes(const McmcParams &P, int tb) { return (size_t)(kEntries * kCopies + P.plan.n * 3 * tb) * sizeof(double); }
 
 // Block size that keeps the most chains resident per SM.
 int mcmc_pick_block(const McmcParams &P, size_t smem_limit, size_t smem_per_sm) {
