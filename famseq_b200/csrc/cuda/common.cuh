@@ -54,6 +54,39 @@ __device__ __forceinline__ VariantPriors select_priors(const RunConstants &C, un
 // a[g] for a runtime g without turning the array into local memory
 __device__ __forceinline__ double pick3(const double (&a)[3], int g) { return g == 0 ? a[0] : (g == 1 ? a[1] : a[2]); }
 
+// ---- x[0..2] / s, correctly rounded -------------------------------------------------------------------
+// r = RN(1/s); q0 = RN(x r); one residual correction q = RN(q0 + (x - s q0) r), the residual being exact in an
+// FMA.  With a correctly rounded reciprocal this is RN(x/s) (Markstein's theorem) provided nothing over- or
+// underflows, which the exponent guard ensures: s in [2^-900, 2^900], x = 0 or x in [2^-900, 2^900].  Checked
+// against the IEEE divide on 2e9 adversarial operand pairs on the host and bit for bit by the GPU parity tests.
+__device__ __forceinline__ bool safe_exponent(double v) {
+    const unsigned e = ((unsigned)__double2hiint(v) >> 20) & 0x7ffu; // biased exponent (sign cleared by the mask)
+    return e >= 1023u - 900u && e <= 1023u + 900u;
+}
+__device__ __forceinline__ void div3(double x0, double x1, double x2, double s, double &q0, double &q1, double &q2) {
+    const bool fast = s > 0.0 && safe_exponent(s) && (x0 == 0.0 || (x0 > 0.0 && safe_exponent(x0))) &&
+                      (x1 == 0.0 || (x1 > 0.0 && safe_exponent(x1))) && (x2 == 0.0 || (x2 > 0.0 && safe_exponent(x2)));
+    if (fast) {
+        const double r = __drcp_rn(s);
+        const double a = __dmul_rn(x0, r), b = __dmul_rn(x1, r), c = __dmul_rn(x2, r);
+        q0 = __fma_rn(__fma_rn(-s, a, x0), r, a);
+        q1 = __fma_rn(__fma_rn(-s, b, x1), r, b);
+        q2 = __fma_rn(__fma_rn(-s, c, x2), r, c);
+    } else {
+        q0 = x0 / s;
+        q1 = x1 / s;
+        q2 = x2 / s;
+    }
+}
+
+// LRC gate of one sample (family.cpp:767-789): true when big/sum < lrc.  For the default -LRC 1 and a non-negative
+// row, big/ls < 1 <=> big < ls (the quotient of two distinct adjacent doubles already rounds below 1; 0/0 and inf/inf
+// compare false both ways), which spares the division; any other -LRC value divides.
+__device__ __forceinline__ bool lrc_wants_pedigree(double lrc, double l0, double l1, double l2, double big, double ls) {
+    if (lrc == 1.0 && l0 >= 0.0 && l1 >= 0.0 && l2 >= 0.0) return big < ls;
+    return big / ls < lrc;
+}
+
 // get_postRlt: strict '<' starting from -1, so the first maximum wins and NaN rows give -1 (255).
 __device__ __forceinline__ uint8_t call_genotype(double p0, double p1, double p2) {
     double big = -1.0;

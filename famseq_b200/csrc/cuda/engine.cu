@@ -286,6 +286,19 @@ int fs_get_tables(const fs_engine *e, double *pcp2, double *pcp2_xf, double *pcp
     return FS_OK;
 }
 
+int fs_get_es_program(const fs_engine *e, uint32_t *words, int32_t capacity, int32_t *n_words, int32_t *n_slots) {
+    if (!e) return fail(FS_E_ARG, "fs_get_es_program: null engine");
+    if (e->es_rc != FS_OK && e->es_rc != FS_E_TOO_LARGE) return fail(e->es_rc, e->es_err);
+    const EsProgram &p = e->es.prog;
+    if (n_words) *n_words = p.n_words;
+    if (n_slots) *n_slots = p.n_slots;
+    if (words) {
+        if (capacity < p.n_words) return fail(FS_E_ARG, "fs_get_es_program: buffer too small");
+        std::memcpy(words, p.words, sizeof(uint32_t) * (size_t)p.n_words);
+    }
+    return FS_OK;
+}
+
 void *fs_alloc_pinned(size_t bytes) {
     void *p = nullptr;
     if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {

@@ -162,8 +162,7 @@ __device__ bool es_interpret(const EsParams &P, const EsThread<TB> &t, double *p
             if (sum == 0.0) failed = true;
             if ((w0 >> 8) & 1u) {
                 const int col = w0 >> 9;
-#pragma unroll
-                for (int g = 0; g < 3; g++) post_row[col * 3 + g] = m[g] / sum;
+                div3(m[0], m[1], m[2], sum, post_row[col * 3], post_row[col * 3 + 1], post_row[col * 3 + 2]);
             }
             pc += 3;
         }
@@ -216,15 +215,13 @@ template <int TB> __global__ void __launch_bounds__(TB) es_kernel(const __grid_c
             const double r2 = l2 * (male ? t.pr.m[2] : t.pr.a[2]);
             const double rs = (r0 + r1) + r2;
             if (rs <= 0.0) failed = true;
-            single_row[c * 3] = r0 / rs;
-            single_row[c * 3 + 1] = r1 / rs;
-            single_row[c * 3 + 2] = r2 / rs;
+            div3(r0, r1, r2, rs, single_row[c * 3], single_row[c * 3 + 1], single_row[c * 3 + 2]);
             double big = 0.0;
             if (big < l0) big = l0;
             if (big < l1) big = l1;
             if (big < l2) big = l2;
             const double ls = (l0 + l1) + l2;
-            if (big / ls < C.lrc) pedigree_needed = true;
+            if (lrc_wants_pedigree(C.lrc, l0, l1, l2, big, ls)) pedigree_needed = true;
         }
         if (!failed) {
             if (!pedigree_needed) { // family.cpp:1164-1253: FPP := individual-only posterior

@@ -61,31 +61,6 @@ __device__ __forceinline__ void bulk_commit_and_wait_read() {
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// ---- x[0..2] / s, correctly rounded -------------------------------------------------------------------
-// r = RN(1/s); q0 = RN(x r); one residual correction q = RN(q0 + (x - s q0) r), the residual being exact in an
-// FMA.  With a correctly rounded reciprocal this is RN(x/s) (Markstein's theorem) provided nothing over- or
-// underflows, which the exponent guard ensures: s in [2^-900, 2^900], x = 0 or x in [2^-900, 2^900].  Checked
-// against the IEEE divide on 2e9 adversarial operand pairs on the host and bit for bit by the GPU parity tests.
-__device__ __forceinline__ bool safe_exponent(double v) {
-    const unsigned e = ((unsigned)__double2hiint(v) >> 20) & 0x7ffu; // biased exponent (sign cleared by the mask)
-    return e >= 1023u - 900u && e <= 1023u + 900u;
-}
-__device__ __forceinline__ void div3(double x0, double x1, double x2, double s, double &q0, double &q1, double &q2) {
-    const bool fast = s > 0.0 && safe_exponent(s) && (x0 == 0.0 || (x0 > 0.0 && safe_exponent(x0))) &&
-                      (x1 == 0.0 || (x1 > 0.0 && safe_exponent(x1))) && (x2 == 0.0 || (x2 > 0.0 && safe_exponent(x2)));
-    if (fast) {
-        const double r = __drcp_rn(s);
-        const double a = __dmul_rn(x0, r), b = __dmul_rn(x1, r), c = __dmul_rn(x2, r);
-        q0 = __fma_rn(__fma_rn(-s, a, x0), r, a);
-        q1 = __fma_rn(__fma_rn(-s, b, x1), r, b);
-        q2 = __fma_rn(__fma_rn(-s, c, x2), r, c);
-    } else {
-        q0 = x0 / s;
-        q1 = x1 / s;
-        q2 = x2 / s;
-    }
-}
-
 template <bool X> __device__ __forceinline__ double trans(const RunConstants &C, int sel, int g, int a, int b) {
     return X ? C.tab[sel][g * 9 + a * 3 + b] : C.tab[0][g * 9 + a * 3 + b];
 }
@@ -266,13 +241,7 @@ __global__ void __launch_bounds__(TB) es_nuclear_kernel(const __grid_constant__ 
             if (big < l1) big = l1;
             if (big < l2) big = l2;
             const double ls = (l0 + l1) + l2;
-            // big/ls < 1 <=> big < ls for non-negative likelihoods (the quotient of two distinct adjacent doubles
-            // already rounds below 1; 0/0, inf/inf compare false both ways); any other -LRC value divides.
-            if (C.lrc == 1.0 && l0 >= 0.0 && l1 >= 0.0 && l2 >= 0.0) {
-                if (big < ls) pedigree_needed = true;
-            } else if (big / ls < C.lrc) {
-                pedigree_needed = true;
-            }
+            if (lrc_wants_pedigree(C.lrc, l0, l1, l2, big, ls)) pedigree_needed = true;
         }
         if (!failed) {
             if (!pedigree_needed) {

@@ -96,6 +96,8 @@ def lib() -> ctypes.CDLL:
         L.fs_free_pinned.argtypes = [P]
         L.fs_last_kernel_ms.restype = D
         L.fs_last_kernel_ms.argtypes = [P]
+        L.fs_get_es_program.restype = ctypes.c_int
+        L.fs_get_es_program.argtypes = [P, P, I32, P, P]
         L.fs_bench_fp64_tflops.restype = ctypes.c_int
         L.fs_bench_fp64_tflops.argtypes = [ctypes.c_int, P]
         _lib = L
@@ -104,7 +106,7 @@ def lib() -> ctypes.CDLL:
 
 EXPORTED_SYMBOLS = ["fs_default_params", "fs_device_count", "fs_create", "fs_destroy", "fs_last_error", "fs_run",
                     "fs_run_device", "fs_get_info", "fs_get_tables", "fs_alloc_pinned", "fs_free_pinned",
-                    "fs_last_kernel_ms", "fs_bench_fp64_tflops"]
+                    "fs_last_kernel_ms", "fs_bench_fp64_tflops", "fs_get_es_program"]
 
 
 def _check(rc: int) -> None:
@@ -173,6 +175,14 @@ class Engine:
         mo, fa = np.zeros(self.n, np.int32), np.zeros(self.n, np.int32)
         _check(lib().fs_get_tables(self._h, _ptr(a), _ptr(xf), _ptr(xm), _ptr(mo), _ptr(fa)))
         return a, xf, xm, mo, fa
+
+    def es_program(self):
+        """(words, n_slots) of the compiled Elston-Stewart message program (introspection, see es_program.hpp)."""
+        n_words, n_slots = ctypes.c_int32(0), ctypes.c_int32(0)
+        _check(lib().fs_get_es_program(self._h, None, 0, ctypes.byref(n_words), ctypes.byref(n_slots)))
+        words = np.zeros(n_words.value, np.uint32)
+        _check(lib().fs_get_es_program(self._h, _ptr(words), n_words.value, None, None))
+        return words, int(n_slots.value)
 
     def last_kernel_ms(self) -> float:
         return float(lib().fs_last_kernel_ms(self._h))

@@ -132,6 +132,11 @@ int fs_get_info(const fs_engine *e, fs_info *out);
 int fs_get_tables(const fs_engine *e, double *pcp2, double *pcp2_xf, double *pcp2_xm, int32_t *mother,
                   int32_t *father);
 
+/* Copies the compiled Elston-Stewart message program (host/es_program.hpp describes the word format) into
+ * `words` (capacity in words); *n_words / *n_slots receive its length and scratch size.  Introspection only:
+ * tests interpret it on the CPU to check the pedigree compiler without a GPU.  FS_E_LOOP on looped pedigrees. */
+int fs_get_es_program(const fs_engine *e, uint32_t *words, int32_t capacity, int32_t *n_words, int32_t *n_slots);
+
 /* Pinned host memory helpers for callers without their own CUDA runtime binding. */
 void *fs_alloc_pinned(size_t bytes);
 void fs_free_pinned(void *p);
