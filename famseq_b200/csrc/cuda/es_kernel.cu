@@ -6,12 +6,12 @@
 // every thread interprets in lock step for its own variant, so there is no divergence and no
 // per-variant allocation.
 //
-// Data movement (the kernel is HBM-bound for small pedigrees):
-//   * a block owns TB consecutive variants = one contiguous [TB][S][3] FP64 tile of the input; it is
-//     copied to shared memory with 16-byte streaming loads (fully coalesced) and read back per thread;
-//   * message 3-vectors live in shared memory as [slot][g][thread] (conflict-free);
-//   * post / single / gt tiles are staged in shared memory and written back as contiguous 16-byte
-//     streaming stores.
+// This is the path of multi-generation pedigrees (nuclear families take es_nuclear_kernel.cu): the work per
+// variant (one 27-term contraction per message) dominates its 73*S+2 bytes, so
+//   * message 3-vectors live in shared memory as [slot][g][thread] (conflict-free, liveness-compacted by the
+//     host compiler) and shared memory is spent on nothing else, to keep as many variants in flight as possible;
+//   * a thread reads its variant's likelihood rows through the read-only path when a message needs them and
+//     writes its post / single / gt rows directly.
 // Arithmetic: this file is compiled with -fmad=false and every product is formed in the reference's
 // association order, so the FP64 results are bit-identical to the reference CPU build.
 #include "common.cuh"
@@ -26,7 +26,7 @@ template <bool X> __device__ __forceinline__ double trans(const RunConstants &C,
 }
 
 template <int TB> struct EsThread {
-    const double *in_row; // this variant's [S][3] likelihoods in shared memory
+    const double *in_row; // this variant's [S][3] likelihoods (global memory, read-only path)
     double *slot;         // base of the [slot][g][TB] scratch, already offset by the thread index
     VariantPriors pr;
 
@@ -37,7 +37,7 @@ template <int TB> struct EsThread {
             for (int g = 0; g < 3; g++) v[g] = slot[(idx * 3 + g) * TB];
         } else if (kind == ES_REF_LK) {
 #pragma unroll
-            for (int g = 0; g < 3; g++) v[g] = in_row[idx * 3 + g];
+            for (int g = 0; g < 3; g++) v[g] = __ldg(in_row + idx * 3 + g);
         } else if (kind == ES_REF_PRIOR) {
 #pragma unroll
             for (int g = 0; g < 3; g++) v[g] = idx ? pr.m[g] : pr.a[g];
@@ -174,109 +174,70 @@ template <int TB> __global__ void __launch_bounds__(TB) es_kernel(const __grid_c
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const RunConstants &C = P.C;
     const int S = C.s, S3 = 3 * S;
-    double *s_in = reinterpret_cast<double *>(smem_raw); // [TB][S][3], same layout as global
-    double *s_post = s_in + TB * S3;
-    double *s_single = s_post + TB * S3;
-    double *s_slot = s_single + TB * S3; // [n_slots][3][TB]
-    uint8_t *s_gt = reinterpret_cast<uint8_t *>(s_slot + (size_t)P.prog.n_slots * 3 * TB); // [TB][S]
-    uint8_t *s_status = s_gt + TB * S;                                                     // [TB]
+    double *s_slot = reinterpret_cast<double *>(smem_raw); // [n_slots][3][TB] message scratch
 
     const int tid = threadIdx.x;
-    const int64_t v0 = (int64_t)blockIdx.x * TB;
-    const int nv = (int)min((int64_t)TB, B.V - v0);
-    const int ndbl = nv * S3;
+    const int64_t v = (int64_t)blockIdx.x * TB + tid;
+    if (v >= B.V) return;
+    // Pedigrees that reach this kernel are multi-generation ones: compute per variant dominates and the variant's
+    // rows (24*S bytes in, 48*S out) are read and written directly; shared memory is kept for the message scratch
+    // so that as many variants as possible are in flight per SM.
+    const unsigned flag = B.flags ? B.flags[v] : 0u;
+    EsThread<TB> t;
+    t.in_row = B.lk + v * S3;
+    t.slot = s_slot + tid;
+    t.pr = select_priors(C, flag);
+    double *post_row = B.post + v * S3;
+    double *single_row = B.single + v * S3;
+    uint8_t *gt_row = B.gt + v * S;
 
-    { // tile load: contiguous, 16-byte, streaming
-        const double *gin = B.lk + v0 * S3;
-        const double2 *g2 = reinterpret_cast<const double2 *>(gin);
-        double2 *s2 = reinterpret_cast<double2 *>(s_in);
-        for (int k = tid; k < (ndbl >> 1); k += TB) s2[k] = __ldcs(g2 + k);
-        if (tid == 0 && (ndbl & 1)) s_in[ndbl - 1] = __ldcs(gin + ndbl - 1);
+    // individual-only posterior (family.cpp:1405-1499) and LRC gate (family.cpp:1140-1162)
+    bool failed = C.unseq_fail[flag & 3u] != 0;
+    bool pedigree_needed = false;
+    for (int c = 0; c < S; c++) {
+        const double l0 = __ldg(t.in_row + c * 3), l1 = __ldg(t.in_row + c * 3 + 1), l2 = __ldg(t.in_row + c * 3 + 2);
+        const bool male = C.col_male[c] != 0;
+        const double r0 = l0 * (male ? t.pr.m[0] : t.pr.a[0]);
+        const double r1 = l1 * (male ? t.pr.m[1] : t.pr.a[1]);
+        const double r2 = l2 * (male ? t.pr.m[2] : t.pr.a[2]);
+        const double rs = (r0 + r1) + r2;
+        if (rs <= 0.0) failed = true;
+        double q0, q1, q2;
+        div3(r0, r1, r2, rs, q0, q1, q2);
+        single_row[c * 3] = q0;
+        single_row[c * 3 + 1] = q1;
+        single_row[c * 3 + 2] = q2;
+        double big = 0.0;
+        if (big < l0) big = l0;
+        if (big < l1) big = l1;
+        if (big < l2) big = l2;
+        const double ls = (l0 + l1) + l2;
+        if (lrc_wants_pedigree(C.lrc, l0, l1, l2, big, ls)) pedigree_needed = true;
     }
-    __syncthreads();
-
-    if (tid < nv) {
-        const unsigned flag = B.flags ? B.flags[v0 + tid] : 0u;
-        EsThread<TB> t;
-        t.in_row = s_in + tid * S3;
-        t.slot = s_slot + tid;
-        t.pr = select_priors(C, flag);
-        double *post_row = s_post + tid * S3;
-        double *single_row = s_single + tid * S3;
-
-        // individual-only posterior (family.cpp:1405-1499) and LRC gate (family.cpp:1140-1162)
-        bool failed = C.unseq_fail[flag & 3u] != 0;
-        bool pedigree_needed = false;
-        for (int c = 0; c < S; c++) {
-            const double l0 = t.in_row[c * 3], l1 = t.in_row[c * 3 + 1], l2 = t.in_row[c * 3 + 2];
-            const bool male = C.col_male[c] != 0;
-            const double r0 = l0 * (male ? t.pr.m[0] : t.pr.a[0]);
-            const double r1 = l1 * (male ? t.pr.m[1] : t.pr.a[1]);
-            const double r2 = l2 * (male ? t.pr.m[2] : t.pr.a[2]);
-            const double rs = (r0 + r1) + r2;
-            if (rs <= 0.0) failed = true;
-            div3(r0, r1, r2, rs, single_row[c * 3], single_row[c * 3 + 1], single_row[c * 3 + 2]);
-            double big = 0.0;
-            if (big < l0) big = l0;
-            if (big < l1) big = l1;
-            if (big < l2) big = l2;
-            const double ls = (l0 + l1) + l2;
-            if (lrc_wants_pedigree(C.lrc, l0, l1, l2, big, ls)) pedigree_needed = true;
-        }
-        if (!failed) {
-            if (!pedigree_needed) { // family.cpp:1164-1253: FPP := individual-only posterior
-                for (int k = 0; k < S3; k++) post_row[k] = single_row[k];
-            } else if ((flag >> 1) & 1u) {
-                failed = es_interpret<true, TB>(P, t, post_row);
-            } else {
-                failed = es_interpret<false, TB>(P, t, post_row);
-            }
-        }
-        if (failed) {
-            for (int k = 0; k < S3; k++) {
-                post_row[k] = 0.0;
-                single_row[k] = 0.0;
-            }
-        }
-        for (int c = 0; c < S; c++)
-            s_gt[tid * S + c] = failed ? (uint8_t)255 : call_genotype(post_row[c * 3], post_row[c * 3 + 1], post_row[c * 3 + 2]);
-        s_status[tid] = failed ? 1 : 0;
-    }
-    __syncthreads();
-
-    { // tile store
-        double2 *gp = reinterpret_cast<double2 *>(B.post + v0 * S3);
-        double2 *gs = reinterpret_cast<double2 *>(B.single + v0 * S3);
-        const double2 *sp = reinterpret_cast<const double2 *>(s_post);
-        const double2 *ss = reinterpret_cast<const double2 *>(s_single);
-        for (int k = tid; k < (ndbl >> 1); k += TB) {
-            __stcs(gp + k, sp[k]);
-            __stcs(gs + k, ss[k]);
-        }
-        if (tid == 0 && (ndbl & 1)) {
-            B.post[v0 * S3 + ndbl - 1] = s_post[ndbl - 1];
-            B.single[v0 * S3 + ndbl - 1] = s_single[ndbl - 1];
-        }
-        const int ngt = nv * S;
-        uint8_t *ggt = B.gt + v0 * S;
-        if ((ngt & 3) == 0 && ((reinterpret_cast<uintptr_t>(ggt) & 3u) == 0)) {
-            const uint32_t *s4 = reinterpret_cast<const uint32_t *>(s_gt);
-            uint32_t *g4 = reinterpret_cast<uint32_t *>(ggt);
-            for (int k = tid; k < (ngt >> 2); k += TB) g4[k] = s4[k];
+    if (!failed) {
+        if (!pedigree_needed) { // family.cpp:1164-1253: FPP := individual-only posterior
+            for (int k = 0; k < S3; k++) post_row[k] = single_row[k];
+        } else if ((flag >> 1) & 1u) {
+            failed = es_interpret<true, TB>(P, t, post_row);
         } else {
-            for (int k = tid; k < ngt; k += TB) ggt[k] = s_gt[k];
+            failed = es_interpret<false, TB>(P, t, post_row);
         }
-        if (tid < nv) B.status[v0 + tid] = s_status[tid];
     }
+    if (failed) {
+        for (int k = 0; k < S3; k++) {
+            post_row[k] = 0.0;
+            single_row[k] = 0.0;
+        }
+    }
+    for (int c = 0; c < S; c++)
+        gt_row[c] = failed ? (uint8_t)255 : call_genotype(post_row[c * 3], post_row[c * 3 + 1], post_row[c * 3 + 2]);
+    B.status[v] = failed ? 1 : 0;
 }
 
 } // namespace
 
 size_t es_smem_bytes(const EsParams &P, int tb) {
-    const size_t S = (size_t)P.C.s;
-    size_t bytes = 3 * (size_t)tb * S * 3 * sizeof(double);        // in, post, single tiles
-    bytes += (size_t)P.prog.n_slots * 3 * tb * sizeof(double);     // message scratch
-    bytes += (size_t)tb * S + tb;                                  // gt, status
+    const size_t bytes = (size_t)(P.prog.n_slots > 0 ? P.prog.n_slots : 1) * 3 * tb * sizeof(double); // message scratch
     return (bytes + 15) & ~(size_t)15;
 }
 
