@@ -26,6 +26,7 @@
 //     of a half-warp hit 16 different bank pairs;
 //   * persistent blocks loop over tiles of TB variants.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.hpp"
@@ -89,7 +90,10 @@ __device__ __forceinline__ double fast_reciprocal(double s) {
     return x;
 }
 
-template <int TB>
+// WGLOBAL = false: own factors in shared memory (small pedigrees: every chain of a full SM fits).
+// WGLOBAL = true : own factors in the global scratch next to the accumulators, read one member ahead through L2;
+//                  shared memory then only holds the tables and the number of chains per SM is set by registers.
+template <int TB, bool WGLOBAL>
 __global__ void __launch_bounds__(TB) mcmc_kernel(const __grid_constant__ McmcParams P, const BatchPtrs B, int burn, int rep,
                                                   uint64_t seed, int64_t v_offset, double *__restrict__ scratch, int n_tiles) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -107,8 +111,9 @@ __global__ void __launch_bounds__(TB) mcmc_kernel(const __grid_constant__ McmcPa
     __syncthreads();
     const uint32_t tab_addr = (uint32_t)__cvta_generic_to_shared(s_tab) + (uint32_t)(lane & (kCopies - 1)) * 8u;
     const uint32_t w_addr = (uint32_t)__cvta_generic_to_shared(s_w) + (uint32_t)tid * 8u;
-    double *w = s_w + tid;
-    double *acc = scratch + (size_t)blockIdx.x * ((size_t)N * 3 * TB) + tid; // [member][g][TB], private to this thread
+    double *acc = scratch + (size_t)blockIdx.x * ((size_t)N * 3 * TB * (WGLOBAL ? 2 : 1)) + tid; // [member][g][TB], thread-private
+    double *wg = acc + (size_t)N * 3 * TB;                                                       // WGLOBAL: own factors
+    double *w = WGLOBAL ? wg : s_w + tid;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -188,14 +193,33 @@ __global__ void __launch_bounds__(TB) mcmc_kernel(const __grid_constant__ McmcPa
         // The step is written branch-light: founders and missing children multiply by a row of ones, the first two
         // children are handled in line, shared memory is addressed with 32-bit shared-window addresses.
         asm volatile("" ::: "memory");
+        double nw0 = 0.0, nw1 = 0.0, nw2 = 0.0; // WGLOBAL: own factors of the next member, fetched one step ahead
+        if constexpr (WGLOBAL) {
+            nw0 = __ldcg(wg);
+            nw1 = __ldcg(wg + TB);
+            nw2 = __ldcg(wg + 2 * TB);
+        }
         const int total_sweeps = burn + rep;
         for (int sweep = 1; sweep <= total_sweeps; sweep++) {
             const bool sampling = sweep > burn;
             for (int i = 0; i < N; i++) {
                 const uint32_t d = pl.member[i];
                 const bool male = (d >> 13) & 1u, founder = (d >> 12) & 1u;
-                const uint32_t wa = w_addr + (uint32_t)i * (3u * TB * 8u);
-                double w0 = lds64(wa), w1 = lds64(wa + TB * 8), w2 = lds64(wa + 2 * TB * 8);
+                double w0, w1, w2;
+                if constexpr (WGLOBAL) {
+                    w0 = nw0;
+                    w1 = nw1;
+                    w2 = nw2;
+                    const double *nx = wg + (size_t)(((i + 1 < N) ? i + 1 : 0) * 3 * TB);
+                    nw0 = __ldcg(nx);
+                    nw1 = __ldcg(nx + TB);
+                    nw2 = __ldcg(nx + 2 * TB);
+                } else {
+                    const uint32_t wa = w_addr + (uint32_t)i * (3u * TB * 8u);
+                    w0 = lds64(wa);
+                    w1 = lds64(wa + TB * 8);
+                    w2 = lds64(wa + 2 * TB * 8);
+                }
                 const int xkind = male ? 2 * 27 : 27; // chrX table of this member / of a child, by sex
                 {   // own factor: transmission from the parents' current genotypes (a row of ones for founders)
                     const int row = cur.get(d & 63u) * 3 + cur.get((d >> 6) & 63u);
@@ -275,23 +299,29 @@ __global__ void __launch_bounds__(TB) mcmc_kernel(const __grid_constant__ McmcPa
     }
 }
 
-template <int TB> cudaError_t launch_tb(const McmcParams &P, const BatchPtrs &B, int burn, int rep, uint64_t seed, int64_t v_offset,
-                                        int sm_count, cudaStream_t stream) {
-    const size_t smem = mcmc_smem_bytes(P, TB);
-    cudaError_t rc = cudaFuncSetAttribute(mcmc_kernel<TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <int TB, bool WGLOBAL>
+cudaError_t launch_tb(const McmcParams &P, const BatchPtrs &B, int burn, int rep, uint64_t seed, int64_t v_offset, int sm_count,
+                      cudaStream_t stream) {
+    const size_t smem = WGLOBAL ? (size_t)kEntries * kCopies * sizeof(double) : mcmc_smem_bytes(P, TB);
+    cudaError_t rc = cudaFuncSetAttribute(mcmc_kernel<TB, WGLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) return rc;
     int per_sm = 0;
-    rc = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mcmc_kernel<TB>, TB, smem);
+    rc = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mcmc_kernel<TB, WGLOBAL>, TB, smem);
     if (rc != cudaSuccess) return rc;
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
+    if (WGLOBAL) { // resident blocks per SM (measured on ped40: 1 -> 1.60e5, 2 -> 1.63e5, 3 -> 1.79e5 variants/s)
+        int cap = 3;
+        if (const char *env = std::getenv("FAMSEQ_MCMC_BLOCKS")) cap = std::max(1, std::atoi(env));
+        per_sm = std::min(per_sm, cap);
+    }
     const int64_t n_tiles = (B.V + TB - 1) / TB;
     if (n_tiles > 0x7fffffff) return cudaErrorInvalidValue;
     const int grid = (int)std::min<int64_t>(n_tiles, (int64_t)sm_count * per_sm);
-    // accumulators: [grid][N][3][TB] doubles, stream-ordered allocation (stays in L2: 32 MB for a full B200)
+    // thread-private chain state: [grid][N][3][TB] accumulators (+ as many own factors when WGLOBAL), stream-ordered
     double *scratch = nullptr;
-    rc = cudaMallocAsync(&scratch, (size_t)grid * P.plan.n * 3 * TB * sizeof(double), stream);
+    rc = cudaMallocAsync(&scratch, (size_t)grid * P.plan.n * 3 * TB * sizeof(double) * (WGLOBAL ? 2 : 1), stream);
     if (rc != cudaSuccess) return rc;
-    mcmc_kernel<TB><<<grid, TB, smem, stream>>>(P, B, burn, rep, seed, v_offset, scratch, (int)n_tiles);
+    mcmc_kernel<TB, WGLOBAL><<<grid, TB, smem, stream>>>(P, B, burn, rep, seed, v_offset, scratch, (int)n_tiles);
     rc = cudaGetLastError();
     const cudaError_t rc2 = cudaFreeAsync(scratch, stream);
     return rc != cudaSuccess ? rc : rc2;
@@ -320,15 +350,19 @@ int mcmc_pick_block(const McmcParams &P, size_t smem_limit, size_t smem_per_sm) 
 cudaError_t launch_mcmc(const McmcParams &P, const BatchPtrs &B, int tb, int burn, int rep, uint64_t seed, int64_t v_offset,
                         int sm_count, cudaStream_t stream) {
     if (B.V <= 0) return cudaSuccess;
+    // Large pedigrees: the own factors of fewer than 512 chains fit in an SM's shared memory -> keep them in L2 instead.
+    bool wglobal = tb < 256;
+    if (const char *env = std::getenv("FAMSEQ_MCMC_WGLOBAL")) wglobal = env[0] == '1';
+    if (wglobal) return launch_tb<256, true>(P, B, burn, rep, seed, v_offset, sm_count, stream);
     switch (tb) {
-    case 256: return launch_tb<256>(P, B, burn, rep, seed, v_offset, sm_count, stream);
-    case 224: return launch_tb<224>(P, B, burn, rep, seed, v_offset, sm_count, stream);
-    case 192: return launch_tb<192>(P, B, burn, rep, seed, v_offset, sm_count, stream);
-    case 160: return launch_tb<160>(P, B, burn, rep, seed, v_offset, sm_count, stream);
-    case 128: return launch_tb<128>(P, B, burn, rep, seed, v_offset, sm_count, stream);
-    case 96: return launch_tb<96>(P, B, burn, rep, seed, v_offset, sm_count, stream);
-    case 64: return launch_tb<64>(P, B, burn, rep, seed, v_offset, sm_count, stream);
-    case 32: return launch_tb<32>(P, B, burn, rep, seed, v_offset, sm_count, stream);
+    case 256: return launch_tb<256, false>(P, B, burn, rep, seed, v_offset, sm_count, stream);
+    case 224: return launch_tb<224, false>(P, B, burn, rep, seed, v_offset, sm_count, stream);
+    case 192: return launch_tb<192, false>(P, B, burn, rep, seed, v_offset, sm_count, stream);
+    case 160: return launch_tb<160, false>(P, B, burn, rep, seed, v_offset, sm_count, stream);
+    case 128: return launch_tb<128, false>(P, B, burn, rep, seed, v_offset, sm_count, stream);
+    case 96: return launch_tb<96, false>(P, B, burn, rep, seed, v_offset, sm_count, stream);
+    case 64: return launch_tb<64, false>(P, B, burn, rep, seed, v_offset, sm_count, stream);
+    case 32: return launch_tb<32, false>(P, B, burn, rep, seed, v_offset, sm_count, stream);
     default: return cudaErrorInvalidValue;
     }
 }
