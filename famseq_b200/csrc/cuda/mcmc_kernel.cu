@@ -16,10 +16,12 @@
 // Gibbs step and on-chip bytes per chain.
 //   * all threads of a warp work on the same member: control flow is uniform, pedigree metadata are one
 //     uniform constant-bank word per member and per parent-child link (host/mcmc_plan.cpp);
-//   * the own factors (3N doubles per chain) live in shared memory as [member][g][thread]; the 3N
-//     accumulators do NOT: they live in an L2-resident global scratch ([block][member][g][thread], 32 MB for
-//     a full GPU) and are updated with fire-and-forget red.global.add.f64 -- three coalesced instructions per
-//     step, off the dependency chain -- which doubles the number of chains an SM holds;
+//   * the 3N accumulators live in a global scratch ([block][member][g][thread], thread-private, coalesced) and
+//     are updated with fire-and-forget red.global.add.f64 -- three instructions per step, off the dependency
+//     chain; the 3N own factors live in shared memory as [member][g][thread] when a full SM's worth of chains
+//     fits (small pedigrees), otherwise in the same scratch, fetched one member ahead through L2, so that the
+//     number of chains in flight is set by registers (24 warps/SM) and not by shared memory (7 warps/SM for 40
+//     members);
 //   * the draw is decided on un-normalised weights (rd*sum < w0, rd*sum > sum - w2), so the reciprocal
 //     (MUFU seed + two Newton steps) is off the critical path;
 //   * the transmission tables are replicated 16 times in shared memory so that the data-dependent look-ups
