@@ -59,7 +59,7 @@ struct fs_engine {
     int es_rc = FS_OK;
     std::string es_err;
     int es_tb = 0;
-    NuclearParams nuclear;      // register-resident fast path for (father, mother, <= 3 childless children)
+    NuclearParams nuclear;      // register-resident fast path for (father, mother, <= 5 childless children)
     bool is_nuclear = false;
     bool force_generic_es = false; // FAMSEQ_ES_GENERIC=1: run nuclear families through the message-program interpreter too
 

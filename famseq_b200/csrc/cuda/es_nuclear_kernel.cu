@@ -1,4 +1,4 @@
-// es_nuclear_kernel.cu -- Elston-Stewart peeling for NUCLEAR FAMILIES (two founders and their C <= 3
+// es_nuclear_kernel.cu -- Elston-Stewart peeling for NUCLEAR FAMILIES (two founders and their C <= 5
 // childless children: trios, quads, ...), the pedigree shape of almost every real FamSeq run and of the
 // headline benchmark (BASELINE.json: 10 M-variant trio).  One variant per thread, everything in registers.
 //
@@ -298,6 +298,8 @@ cudaError_t launch_es_nuclear(const NuclearParams &P, const BatchPtrs &B, cudaSt
     case 1: return launch_nc<1, 128>(P, B, stream);
     case 2: return launch_nc<2, 128>(P, B, stream);
     case 3: return launch_nc<3, 128>(P, B, stream);
+    case 4: return launch_nc<4, 128>(P, B, stream);
+    case 5: return launch_nc<5, 128>(P, B, stream);
     default: return cudaErrorInvalidValue;
     }
 }

@@ -22,7 +22,7 @@ int es_pick_block(const EsParams &P, size_t smem_limit);
 cudaError_t launch_es(const EsParams &P, const BatchPtrs &B, int tb, cudaStream_t stream);
 
 // ---- Elston-Stewart, nuclear families (es_nuclear_kernel.cu) -------------------------------------------
-constexpr int ES_NUCLEAR_MAX_CHILDREN = 3;
+constexpr int ES_NUCLEAR_MAX_CHILDREN = 5;
 struct NuclearParams {
     RunConstants C;
     int32_t n_children;

@@ -268,7 +268,7 @@ def _wide_likelihoods(V, S, seed):
     return lk
 
 
-@pytest.mark.parametrize("n_children", [1, 2, 3])
+@pytest.mark.parametrize("n_children", [1, 2, 3, 4, 5])
 def test_nuclear_fast_path_is_bit_identical(n_children, monkeypatch):
     rows = [(1, 0, 0, 1), (2, 0, 0, 2)] + [(3 + k, 2, 1, 1 + k % 2) for k in range(n_children)]
     ped = synth._mk(rows)
