@@ -9,11 +9,16 @@
 // This is the path of multi-generation pedigrees (nuclear families take es_nuclear_kernel.cu): the work per
 // variant (one 27-term contraction per message) dominates its 73*S+2 bytes, so
 //   * message 3-vectors live in shared memory as [slot][g][thread] (conflict-free, liveness-compacted by the
-//     host compiler) and shared memory is spent on nothing else, to keep as many variants in flight as possible;
-//   * a thread reads its variant's likelihood rows through the read-only path when a message needs them and
-//     writes its post / single / gt rows directly.
+//     host compiler);
+//   * the block's likelihood tile ([TB][S][3], contiguous in HBM) is copied once, coalesced, into shared memory
+//     in transposed form (row stride TB+1: conflict-free for the copy and for the per-thread reads), so a message
+//     that needs a likelihood row pays a shared-memory access, not a global one;
+//   * post / single / gt rows are written directly (write-only, never read back); the block size is the one that
+//     keeps the most variants resident per SM.
 // Arithmetic: this file is compiled with -fmad=false and every product is formed in the reference's
 // association order, so the FP64 results are bit-identical to the reference CPU build.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.hpp"
 
@@ -26,7 +31,7 @@ template <bool X> __device__ __forceinline__ double trans(const RunConstants &C,
 }
 
 template <int TB> struct EsThread {
-    const double *in_row; // this variant's [S][3] likelihoods (global memory, read-only path)
+    const double *in_row; // this variant's likelihoods in shared memory: element k at in_row[k * (TB + 1)]
     double *slot;         // base of the [slot][g][TB] scratch, already offset by the thread index
     VariantPriors pr;
 
@@ -37,7 +42,7 @@ template <int TB> struct EsThread {
             for (int g = 0; g < 3; g++) v[g] = slot[(idx * 3 + g) * TB];
         } else if (kind == ES_REF_LK) {
 #pragma unroll
-            for (int g = 0; g < 3; g++) v[g] = __ldg(in_row + idx * 3 + g);
+            for (int g = 0; g < 3; g++) v[g] = in_row[(idx * 3 + g) * (TB + 1)];
         } else if (kind == ES_REF_PRIOR) {
 #pragma unroll
             for (int g = 0; g < 3; g++) v[g] = idx ? pr.m[g] : pr.a[g];
@@ -54,7 +59,7 @@ template <int TB> struct EsThread {
 // Interprets the message program for one variant.  Returns true when a member's row sum was exactly
 // zero (the reference returns false there, family.cpp:1305-1310).
 template <bool X, int TB>
-__device__ bool es_interpret(const EsParams &P, const EsThread<TB> &t, double *post_row) {
+__device__ bool es_interpret(const EsParams &P, const EsThread<TB> &t, double *post_row, uint8_t *gt_row) {
     const RunConstants &C = P.C;
     bool failed = false;
     int pc = 0;
@@ -162,7 +167,12 @@ __device__ bool es_interpret(const EsParams &P, const EsThread<TB> &t, double *p
             if (sum == 0.0) failed = true;
             if ((w0 >> 8) & 1u) {
                 const int col = w0 >> 9;
-                div3(m[0], m[1], m[2], sum, post_row[col * 3], post_row[col * 3 + 1], post_row[col * 3 + 2]);
+                double q0, q1, q2;
+                div3(m[0], m[1], m[2], sum, q0, q1, q2);
+                post_row[col * 3] = q0;
+                post_row[col * 3 + 1] = q1;
+                post_row[col * 3 + 2] = q2;
+                gt_row[col] = call_genotype(q0, q1, q2); // get_postRlt (family.cpp:636-665), from registers
             }
             pc += 3;
         }
@@ -174,17 +184,26 @@ template <int TB> __global__ void __launch_bounds__(TB) es_kernel(const __grid_c
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const RunConstants &C = P.C;
     const int S = C.s, S3 = 3 * S;
-    double *s_slot = reinterpret_cast<double *>(smem_raw); // [n_slots][3][TB] message scratch
+    double *s_slot = reinterpret_cast<double *>(smem_raw);       // [n_slots][3][TB] message scratch
+    double *s_in = s_slot + (size_t)P.prog.n_slots * 3 * TB;     // [S*3][TB+1] the block's likelihood rows, transposed
 
     const int tid = threadIdx.x;
-    const int64_t v = (int64_t)blockIdx.x * TB + tid;
-    if (v >= B.V) return;
-    // Pedigrees that reach this kernel are multi-generation ones: compute per variant dominates and the variant's
-    // rows (24*S bytes in, 48*S out) are read and written directly; shared memory is kept for the message scratch
-    // so that as many variants as possible are in flight per SM.
+    const int64_t v0 = (int64_t)blockIdx.x * TB;
+    const int nv = (int)min((int64_t)TB, B.V - v0);
+    {   // coalesced copy of the block's contiguous [nv][S][3] tile; row stride TB+1 keeps both the transposing
+        // writes (consecutive k) and the per-thread reads (consecutive threads) free of bank conflicts
+        const double *gin = B.lk + v0 * S3;
+        for (int e = tid; e < nv * S3; e += TB) {
+            const int tt = e / S3, k = e - tt * S3;
+            s_in[k * (TB + 1) + tt] = __ldcs(gin + e);
+        }
+    }
+    __syncthreads();
+    const int64_t v = v0 + tid;
+    if (tid >= nv) return;
     const unsigned flag = B.flags ? B.flags[v] : 0u;
     EsThread<TB> t;
-    t.in_row = B.lk + v * S3;
+    t.in_row = s_in + tid;
     t.slot = s_slot + tid;
     t.pr = select_priors(C, flag);
     double *post_row = B.post + v * S3;
@@ -195,7 +214,7 @@ template <int TB> __global__ void __launch_bounds__(TB) es_kernel(const __grid_c
     bool failed = C.unseq_fail[flag & 3u] != 0;
     bool pedigree_needed = false;
     for (int c = 0; c < S; c++) {
-        const double l0 = __ldg(t.in_row + c * 3), l1 = __ldg(t.in_row + c * 3 + 1), l2 = __ldg(t.in_row + c * 3 + 2);
+        const double l0 = t.in_row[(c * 3) * (TB + 1)], l1 = t.in_row[(c * 3 + 1) * (TB + 1)], l2 = t.in_row[(c * 3 + 2) * (TB + 1)];
         const bool male = C.col_male[c] != 0;
         const double r0 = l0 * (male ? t.pr.m[0] : t.pr.a[0]);
         const double r1 = l1 * (male ? t.pr.m[1] : t.pr.a[1]);
@@ -207,6 +226,7 @@ template <int TB> __global__ void __launch_bounds__(TB) es_kernel(const __grid_c
         single_row[c * 3] = q0;
         single_row[c * 3 + 1] = q1;
         single_row[c * 3 + 2] = q2;
+        gt_row[c] = call_genotype(q0, q1, q2); // stands when the gate keeps the pedigree out; FIN overwrites it otherwise
         double big = 0.0;
         if (big < l0) big = l0;
         if (big < l1) big = l1;
@@ -218,9 +238,9 @@ template <int TB> __global__ void __launch_bounds__(TB) es_kernel(const __grid_c
         if (!pedigree_needed) { // family.cpp:1164-1253: FPP := individual-only posterior
             for (int k = 0; k < S3; k++) post_row[k] = single_row[k];
         } else if ((flag >> 1) & 1u) {
-            failed = es_interpret<true, TB>(P, t, post_row);
+            failed = es_interpret<true, TB>(P, t, post_row, gt_row);
         } else {
-            failed = es_interpret<false, TB>(P, t, post_row);
+            failed = es_interpret<false, TB>(P, t, post_row, gt_row);
         }
     }
     if (failed) {
@@ -228,25 +248,34 @@ template <int TB> __global__ void __launch_bounds__(TB) es_kernel(const __grid_c
             post_row[k] = 0.0;
             single_row[k] = 0.0;
         }
+        for (int c = 0; c < S; c++) gt_row[c] = 255;
     }
-    for (int c = 0; c < S; c++)
-        gt_row[c] = failed ? (uint8_t)255 : call_genotype(post_row[c * 3], post_row[c * 3 + 1], post_row[c * 3 + 2]);
     B.status[v] = failed ? 1 : 0;
 }
 
 } // namespace
 
 size_t es_smem_bytes(const EsParams &P, int tb) {
-    const size_t bytes = (size_t)(P.prog.n_slots > 0 ? P.prog.n_slots : 1) * 3 * tb * sizeof(double); // message scratch
+    size_t bytes = (size_t)P.prog.n_slots * 3 * tb * sizeof(double);   // message scratch
+    bytes += (size_t)P.C.s * 3 * (tb + 1) * sizeof(double);            // the block's likelihood rows
     return (bytes + 15) & ~(size_t)15;
 }
 
 // Picks the largest block the scratch fits in (more threads per SM hide FP64 and LDS latency).
 int es_pick_block(const EsParams &P, size_t smem_limit) {
+    // the block size that keeps the most variants resident per SM (registers allow 512 threads)
     const int candidates[] = {128, 64, 32};
-    for (int tb : candidates)
-        if (es_smem_bytes(P, tb) <= smem_limit) return tb;
-    return 0;
+    int best = 0, best_threads = 0;
+    for (int tb : candidates) {
+        const size_t need = es_smem_bytes(P, tb) + 1024;
+        if (need > smem_limit + 1024) continue;
+        const int threads = (int)std::min<size_t>(512, (smem_limit + 1024) / need * tb);
+        if (threads > best_threads) {
+            best_threads = threads;
+            best = tb;
+        }
+    }
+    return best;
 }
 
 cudaError_t launch_es(const EsParams &P, const BatchPtrs &B, int tb, cudaStream_t stream) {
