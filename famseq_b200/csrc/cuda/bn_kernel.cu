@@ -383,6 +383,7 @@ cudaError_t launch_bn(const BnParams &P, const BatchPtrs &B, int sm_count, cudaS
     case 2: return indep ? launch_bn_u<2, true>(P, B, sm_count, stream) : launch_bn_u<2, false>(P, B, sm_count, stream);
     case 3: return indep ? launch_bn_u<3, true>(P, B, sm_count, stream) : launch_bn_u<3, false>(P, B, sm_count, stream);
     case 4: return indep ? launch_bn_u<4, true>(P, B, sm_count, stream) : launch_bn_u<4, false>(P, B, sm_count, stream);
+    case 5: return indep ? launch_bn_u<5, true>(P, B, sm_count, stream) : launch_bn_u<5, false>(P, B, sm_count, stream);
     default: return cudaErrorInvalidValue;
     }
 }

@@ -44,7 +44,11 @@ int build_bn_plan(const Pedigree &ped, BnPlan &out, std::string &err) {
     std::vector<int> level_of(N);
     for (int L = 0; L < N; L++) level_of[order[L]] = L;
 
-    p.u = N < 3 ? N : (N >= 9 ? BN_MAX_UNROLL : 3);
+    int n_leaves = 0;
+    for (int i = 0; i < N; i++) n_leaves += ped.children[i].empty();
+    // fully unrolled depth: 5 (243 configurations per block) only pays when the block can run out of registers,
+    // i.e. when the five innermost members are all childless
+    p.u = N < 3 ? N : (N >= 11 && n_leaves >= 5 ? 5 : (N >= 9 ? 4 : 3));
     if (const char *env = std::getenv("FAMSEQ_BN_UNROLL")) { // tuning knob: depth of the fully unrolled block
         const int u = std::atoi(env);
         if (u >= 1 && u <= BN_MAX_UNROLL && u <= N) p.u = u;

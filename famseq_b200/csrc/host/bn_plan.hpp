@@ -17,7 +17,7 @@
 namespace famseq {
 
 constexpr int BN_MAX_LEVELS = 31; // 2 bits per level in a 64-bit word, field 31 stays zero
-constexpr int BN_MAX_UNROLL = 4;
+constexpr int BN_MAX_UNROLL = 5;
 constexpr int BN_ZERO_SHIFT = 62; // bit position of the always-zero field (founders' "parents")
 
 struct BnPlan {
