@@ -59,13 +59,15 @@ __device__ __forceinline__ double pick3(const double (&a)[3], int g) { return g 
 // FMA.  With a correctly rounded reciprocal this is RN(x/s) (Markstein's theorem) provided nothing over- or
 // underflows, which the exponent guard ensures: s in [2^-900, 2^900], x = 0 or x in [2^-900, 2^900].  Checked
 // against the IEEE divide on 2e9 adversarial operand pairs on the host and bit for bit by the GPU parity tests.
-__device__ __forceinline__ bool safe_exponent(double v) {
-    const unsigned e = ((unsigned)__double2hiint(v) >> 20) & 0x7ffu; // biased exponent (sign cleared by the mask)
-    return e >= 1023u - 900u && e <= 1023u + 900u;
+// The guard runs on the integer pipe (the FP64 pipe is the scarce one): a positive normal divisor with exponent in
+// [-900, 900], every dividend either +-0 or of magnitude in the same range.
+__device__ __forceinline__ bool safe_dividend(double x) {
+    const unsigned hi = (unsigned)__double2hiint(x) & 0x7fffffffu, lo = (unsigned)__double2loint(x);
+    return (hi - ((1023u - 900u) << 20)) <= (1800u << 20) || (hi | lo) == 0u;
 }
 __device__ __forceinline__ void div3(double x0, double x1, double x2, double s, double &q0, double &q1, double &q2) {
-    const bool fast = s > 0.0 && safe_exponent(s) && (x0 == 0.0 || (x0 > 0.0 && safe_exponent(x0))) &&
-                      (x1 == 0.0 || (x1 > 0.0 && safe_exponent(x1))) && (x2 == 0.0 || (x2 > 0.0 && safe_exponent(x2)));
+    const bool fast = ((unsigned)__double2hiint(s) - ((1023u - 900u) << 20)) <= (1800u << 20) // positive (sign bit clear)
+                      & safe_dividend(x0) & safe_dividend(x1) & safe_dividend(x2);
     if (fast) {
         const double r = __drcp_rn(s);
         const double a = __dmul_rn(x0, r), b = __dmul_rn(x1, r), c = __dmul_rn(x2, r);
@@ -79,11 +81,13 @@ __device__ __forceinline__ void div3(double x0, double x1, double x2, double s, 
     }
 }
 
-// LRC gate of one sample (family.cpp:767-789): true when big/sum < lrc.  For the default -LRC 1 and a non-negative
-// row, big/ls < 1 <=> big < ls (the quotient of two distinct adjacent doubles already rounds below 1; 0/0 and inf/inf
-// compare false both ways), which spares the division; any other -LRC value divides.
+// LRC gate of one sample (family.cpp:767-789): true when big/sum < lrc.  For the default -LRC 1 and a row without
+// negative entries (sign bits clear), big/ls < 1 <=> big < ls (the quotient of two distinct adjacent doubles already
+// rounds below 1; 0/0, inf/inf and NaN rows compare false both ways), which spares the division; any other -LRC
+// value divides.
 __device__ __forceinline__ bool lrc_wants_pedigree(double lrc, double l0, double l1, double l2, double big, double ls) {
-    if (lrc == 1.0 && l0 >= 0.0 && l1 >= 0.0 && l2 >= 0.0) return big < ls;
+    const bool no_negative = (__double2hiint(l0) | __double2hiint(l1) | __double2hiint(l2)) >= 0;
+    if (lrc == 1.0 && no_negative) return big < ls;
     return big / ls < lrc;
 }
 

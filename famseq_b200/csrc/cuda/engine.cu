@@ -208,6 +208,8 @@ int fs_create(const fs_pedigree *ped, const fs_params *params, int device, fs_en
                     np.n_children++;
                 }
             e->is_nuclear = true;
+            const char *probe = std::getenv("FAMSEQ_ES_IO_PROBE");
+            np.io_probe = probe && probe[0] == '1';
         }
         const char *env = std::getenv("FAMSEQ_ES_GENERIC");
         e->force_generic_es = env && env[0] == '1';

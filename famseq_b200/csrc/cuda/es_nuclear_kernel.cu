@@ -220,7 +220,11 @@ __global__ void __launch_bounds__(TB) es_nuclear_kernel(const __grid_constant__ 
     else
         __syncthreads();
 
-    if (tid < nv) {
+    if (tid < nv && P.io_probe) { // I/O ceiling probe: same tiles in and out, no arithmetic
+        for (int k = 0; k < S3; k++) s_post[tid * S3 + k] = s_single[tid * S3 + k] = s_in[tid * S3 + k];
+        for (int c = 0; c < S; c++) s_gt[tid * S + c] = 0;
+        s_status[tid] = 0;
+    } else if (tid < nv) {
         const double *in_row = s_in + tid * S3;
         double *post_row = s_post + tid * S3;
         double *single_row = s_single + tid * S3;

@@ -29,6 +29,7 @@ struct NuclearParams {
     int32_t col_father, col_mother;               // input column or -1
     int32_t col_child[ES_NUCLEAR_MAX_CHILDREN];   // children in ped order
     int32_t male_child[ES_NUCLEAR_MAX_CHILDREN];
+    int32_t io_probe; // FAMSEQ_ES_IO_PROBE=1: move the tiles but skip the arithmetic (measures the I/O ceiling; results are garbage)
 };
 cudaError_t launch_es_nuclear(const NuclearParams &P, const BatchPtrs &B, cudaStream_t stream);
 
