@@ -8,11 +8,11 @@
 //
 // This is the path of multi-generation pedigrees (nuclear families take es_nuclear_kernel.cu): the work per
 // variant (one 27-term contraction per message) dominates its 73*S+2 bytes, so
-//   * message 3-vectors live in shared memory as [slot][g][thread] (conflict-free, liveness-compacted by the
-//     host compiler);
-//   * the block's likelihood tile ([TB][S][3], contiguous in HBM) is copied once, coalesced, into shared memory
-//     in transposed form (row stride TB+1: conflict-free for the copy and for the per-thread reads), so a message
-//     that needs a likelihood row pays a shared-memory access, not a global one;
+//   * every operand of the program -- likelihood rows, message scratch (liveness-compacted by the host compiler),
+//     the founder priors, the vector of ones -- lives in one per-variant "vector file" in shared memory and is
+//     addressed by a plain index, so the interpreter fetches an operand with three loads and no case distinction;
+//   * the block's likelihood tile ([TB][S][3], contiguous in HBM) is copied once, coalesced, into that file in
+//     transposed form (row stride TB+1: conflict-free for the copy and for the per-thread accesses);
 //   * post / single / gt rows are written directly (write-only, never read back); the block size is the one that
 //     keeps the most variants resident per SM.
 // Arithmetic: this file is compiled with -fmad=false and every product is formed in the reference's
@@ -30,29 +30,20 @@ template <bool X> __device__ __forceinline__ double trans(const RunConstants &C,
     return X ? C.tab[sel][g * 9 + a * 3 + b] : C.tab[0][g * 9 + a * 3 + b];
 }
 
+// Per-variant vector file in shared memory (operand encoding of host/es_program.hpp): vector u, component g of this
+// thread's variant is vec[(u * 3 + g) * (TB + 1)].  The odd row stride keeps both the transposing tile copy and the
+// per-thread accesses free of bank conflicts.
 template <int TB> struct EsThread {
-    const double *in_row; // this variant's likelihoods in shared memory: element k at in_row[k * (TB + 1)]
-    double *slot;         // base of the [slot][g][TB] scratch, already offset by the thread index
+    double *vec;
     VariantPriors pr;
 
-    __device__ __forceinline__ void load(uint32_t r, double v[3]) const {
-        const uint32_t kind = es_ref_kind(r), idx = es_ref_index(r);
-        if (kind == ES_REF_SLOT) {
+    __device__ __forceinline__ void load(uint32_t u, double v[3]) const {
 #pragma unroll
-            for (int g = 0; g < 3; g++) v[g] = slot[(idx * 3 + g) * TB];
-        } else if (kind == ES_REF_LK) {
-#pragma unroll
-            for (int g = 0; g < 3; g++) v[g] = in_row[(idx * 3 + g) * (TB + 1)];
-        } else if (kind == ES_REF_PRIOR) {
-#pragma unroll
-            for (int g = 0; g < 3; g++) v[g] = idx ? pr.m[g] : pr.a[g];
-        } else {
-            v[0] = v[1] = v[2] = 1.0;
-        }
+        for (int g = 0; g < 3; g++) v[g] = vec[(u * 3 + g) * (TB + 1)];
     }
-    __device__ __forceinline__ void store(uint32_t dst, const double v[3]) const {
+    __device__ __forceinline__ void store(uint32_t u, const double v[3]) const {
 #pragma unroll
-        for (int g = 0; g < 3; g++) slot[(dst * 3 + g) * TB] = v[g];
+        for (int g = 0; g < 3; g++) vec[(u * 3 + g) * (TB + 1)] = v[g];
     }
 };
 
@@ -184,18 +175,16 @@ template <int TB> __global__ void __launch_bounds__(TB) es_kernel(const __grid_c
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const RunConstants &C = P.C;
     const int S = C.s, S3 = 3 * S;
-    double *s_slot = reinterpret_cast<double *>(smem_raw);       // [n_slots][3][TB] message scratch
-    double *s_in = s_slot + (size_t)P.prog.n_slots * 3 * TB;     // [S*3][TB+1] the block's likelihood rows, transposed
+    double *s_vec = reinterpret_cast<double *>(smem_raw); // [(S + n_slots + 3) * 3][TB + 1] vector file
 
     const int tid = threadIdx.x;
     const int64_t v0 = (int64_t)blockIdx.x * TB;
     const int nv = (int)min((int64_t)TB, B.V - v0);
-    {   // coalesced copy of the block's contiguous [nv][S][3] tile; row stride TB+1 keeps both the transposing
-        // writes (consecutive k) and the per-thread reads (consecutive threads) free of bank conflicts
+    {   // coalesced copy of the block's contiguous [nv][S][3] likelihood tile into rows [0, 3S) of the vector file
         const double *gin = B.lk + v0 * S3;
         for (int e = tid; e < nv * S3; e += TB) {
             const int tt = e / S3, k = e - tt * S3;
-            s_in[k * (TB + 1) + tt] = __ldcs(gin + e);
+            s_vec[k * (TB + 1) + tt] = __ldcs(gin + e);
         }
     }
     __syncthreads();
@@ -203,9 +192,15 @@ template <int TB> __global__ void __launch_bounds__(TB) es_kernel(const __grid_c
     if (tid >= nv) return;
     const unsigned flag = B.flags ? B.flags[v] : 0u;
     EsThread<TB> t;
-    t.in_row = s_in + tid;
-    t.slot = s_slot + tid;
+    t.vec = s_vec + tid;
     t.pr = select_priors(C, flag);
+    {   // the three special vectors behind the scratch: prior (non-male), prior (male), ones
+        const uint32_t special = (uint32_t)(S + P.prog.n_slots);
+        const double one[3] = {1.0, 1.0, 1.0};
+        t.store(special, t.pr.a);
+        t.store(special + 1, t.pr.m);
+        t.store(special + 2, one);
+    }
     double *post_row = B.post + v * S3;
     double *single_row = B.single + v * S3;
     uint8_t *gt_row = B.gt + v * S;
@@ -214,7 +209,7 @@ template <int TB> __global__ void __launch_bounds__(TB) es_kernel(const __grid_c
     bool failed = C.unseq_fail[flag & 3u] != 0;
     bool pedigree_needed = false;
     for (int c = 0; c < S; c++) {
-        const double l0 = t.in_row[(c * 3) * (TB + 1)], l1 = t.in_row[(c * 3 + 1) * (TB + 1)], l2 = t.in_row[(c * 3 + 2) * (TB + 1)];
+        const double l0 = t.vec[(c * 3) * (TB + 1)], l1 = t.vec[(c * 3 + 1) * (TB + 1)], l2 = t.vec[(c * 3 + 2) * (TB + 1)];
         const bool male = C.col_male[c] != 0;
         const double r0 = l0 * (male ? t.pr.m[0] : t.pr.a[0]);
         const double r1 = l1 * (male ? t.pr.m[1] : t.pr.a[1]);
@@ -256,8 +251,7 @@ template <int TB> __global__ void __launch_bounds__(TB) es_kernel(const __grid_c
 } // namespace
 
 size_t es_smem_bytes(const EsParams &P, int tb) {
-    size_t bytes = (size_t)P.prog.n_slots * 3 * tb * sizeof(double);   // message scratch
-    bytes += (size_t)P.C.s * 3 * (tb + 1) * sizeof(double);            // the block's likelihood rows
+    const size_t bytes = (size_t)(P.C.s + P.prog.n_slots + 3) * 3 * (tb + 1) * sizeof(double); // the vector file
     return (bytes + 15) & ~(size_t)15;
 }
 

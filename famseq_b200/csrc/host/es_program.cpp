@@ -197,7 +197,6 @@ template <class F> void for_each_ref(Op &o, F f) {
     }
 }
 
-uint32_t enc(const Ref &r) { return es_ref(r.kind, (uint32_t)r.index); }
 
 } // namespace
 
@@ -246,20 +245,36 @@ int compile_es_program(const Pedigree &ped, EsProgram &out, std::string &err) {
         return FS_E_TOO_LARGE;
     }
 
+    // Operand encoding: index of a 3-vector in the per-variant vector file the kernel keeps in shared memory --
+    // [0, S) likelihood rows of the input columns, [S, S + n_slots) message scratch, then the founder prior of a
+    // non-male member, the founder prior of a male member, and the vector of ones.
+    const uint32_t S = (uint32_t)ped.s(), first_slot = S, special = S + (uint32_t)n_phys;
+    auto enc = [&](const Ref &r) -> uint32_t {
+        switch (r.kind) {
+        case ES_REF_LK: return (uint32_t)r.index;
+        case ES_REF_SLOT: return first_slot + (uint32_t)r.index;
+        case ES_REF_PRIOR: return special + (r.index ? 1u : 0u);
+        default: return special + 2u;
+        }
+    };
+    if (special + 3u >= 0xffffu) {
+        err = "pedigree too large for the ES message program (vector file)";
+        return FS_E_TOO_LARGE;
+    }
     std::vector<uint32_t> w;
     for (const Op &o : c.ops) {
         switch (o.op) {
         case ES_OP_MUL:
-            w.push_back(ES_OP_MUL | (uint32_t)o.dst << 8);
+            w.push_back(ES_OP_MUL | (first_slot + (uint32_t)o.dst) << 8);
             w.push_back(enc(o.a) | enc(o.b) << 16);
             break;
         case ES_OP_ANT:
-            w.push_back(ES_OP_ANT | (uint32_t)o.dst << 8 | (uint32_t)o.male << 24 | (uint32_t)o.items.size() << 25);
+            w.push_back(ES_OP_ANT | (first_slot + (uint32_t)o.dst) << 8 | (uint32_t)o.male << 24 | (uint32_t)o.items.size() << 25);
             w.push_back(enc(o.a) | enc(o.b) << 16);
             for (const Item &it : o.items) w.push_back(enc(it.r0) | (uint32_t)it.male << 16);
             break;
         case ES_OP_POS:
-            w.push_back(ES_OP_POS | (uint32_t)o.dst << 8 | (uint32_t)o.male << 24 | (uint32_t)o.items.size() << 25);
+            w.push_back(ES_OP_POS | (first_slot + (uint32_t)o.dst) << 8 | (uint32_t)o.male << 24 | (uint32_t)o.items.size() << 25);
             w.push_back(enc(o.a));
             for (const Item &it : o.items) {
                 w.push_back(enc(it.r0) | enc(it.r1) << 16);

@@ -16,7 +16,13 @@
 
 namespace famseq {
 
-// A "vector reference" names a genotype 3-vector.  16 bits: kind in the top 3 bits, index below.
+// Inside the compiler a "vector reference" names a genotype 3-vector by kind and index.  In the encoded program an
+// operand is a 16-bit index into the per-variant VECTOR FILE the kernel keeps in shared memory:
+//   [0, S)              likelihood rows of the input columns
+//   [S, S + n_slots)    message scratch
+//   S + n_slots + 0/1   founder prior of a non-male / male member (the latter is the chrX male prior on X)
+//   S + n_slots + 2     the vector of ones (an unsequenced member's likelihood, an empty product)
+// so the interpreter fetches any operand with three shared-memory loads and no case distinction.
 enum EsRefKind : uint32_t {
     ES_REF_ONE = 0,   // (1,1,1): an unsequenced member's likelihood / an empty product. Never multiplied.
     ES_REF_SLOT = 1,  // per-thread scratch 3-vector `index`

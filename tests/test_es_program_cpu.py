@@ -12,7 +12,6 @@ from famseq_b200 import synth
 from oracle import oracle as O
 
 OP_END, OP_MUL, OP_ANT, OP_POS, OP_FIN = 0, 1, 2, 3, 4
-REF_ONE, REF_SLOT, REF_LK, REF_PRIOR = 0, 1, 2, 3
 TAB_AUTO, TAB_XF, TAB_XM = 0, 1, 2
 
 
@@ -24,15 +23,12 @@ def interpret(words, n_slots, tabs, priors, lk, flag):
     slots = [[0.0] * 3 for _ in range(n_slots)]
     post = [[0.0] * 3 for _ in range(len(lk))]
 
-    def load(r):
-        kind, idx = (r >> 13) & 7, r & 0x1fff
-        if kind == REF_SLOT:
-            return list(slots[idx])
-        if kind == REF_LK:
-            return [float(x) for x in lk[idx]]
-        if kind == REF_PRIOR:
-            return [float(x) for x in (pm if idx else pa)]
-        return [1.0, 1.0, 1.0]
+    S = len(lk)
+    # vector file: [0,S) likelihood rows, [S,S+n_slots) scratch, then prior (non-male), prior (male), ones
+    slots = [[float(x) for x in row] for row in lk] + slots + [[float(x) for x in pa], [float(x) for x in pm], [1.0, 1.0, 1.0]]
+
+    def load(u):
+        return list(slots[u])
 
     def T(male, g, a, b):
         t = tabs[(TAB_XM if male else TAB_XF) if chrx else TAB_AUTO]
