@@ -2,10 +2,12 @@
 // dispatch to the three method kernels.  One engine drives one GPU; multi-GPU runs use one engine
 // (one process, or one host thread) per device with the variants sharded between them.
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../../include/famseq_b200.h"
@@ -13,6 +15,7 @@
 #include "../host/es_compiler.hpp"
 #include "../host/mcmc_planner.hpp"
 #include "../host/pedigree.hpp"
+#include "gibbs_jit.hpp"
 #include "kernels.hpp"
 
 using namespace famseq;
@@ -45,6 +48,20 @@ struct DeviceChunk {
     int64_t capacity = 0; // variants
     int64_t in_flight = 0;
 };
+
+// Pedigree-specialised Gibbs kernel (gibbs_jit.cu).  FAMSEQ_MCMC_JIT: 0 = never, 1 = compile at the first MCMC batch and
+// wait for it, unset = compile on a worker thread once a batch is large enough to be worth it and run the table-driven
+// kernel until the cubin is ready (both kernels return the same bytes, so the switch is invisible).
+struct GibbsJitState {
+    enum { IDLE, COMPILING, COMPILED, FAILED, LOADED };
+    int mode = 2;
+    double min_work = 1e9; // Gibbs steps (variants x sweeps x members) in one batch before a compile is started
+    std::thread worker;
+    std::atomic<int> state{IDLE};
+    GibbsJitConfig cfg;
+    std::string cubin, log, err;
+    GibbsJitKernel *kernel = nullptr;
+};
 } // namespace
 
 struct fs_engine {
@@ -71,9 +88,10 @@ struct fs_engine {
     int mcmc_rc = FS_OK;
     std::string mcmc_err;
     int mcmc_tb = 0;
+    GibbsJitState jit;
 
     DeviceChunk chunk[kPipelineDepth];
-    int64_t launches = 0;
+    int64_t launches = 0, jit_launches = 0;
     double last_kernel_ms = 0;
 };
 
@@ -119,8 +137,10 @@ static void release_chunks(fs_engine *e) {
 
 void fs_destroy(fs_engine *e) {
     if (!e) return;
+    if (e->jit.worker.joinable()) e->jit.worker.join();
     if (e->device >= 0) {
         cudaSetDevice(e->device);
+        gibbs_jit_unload(e->jit.kernel);
         release_chunks(e);
     }
     delete e;
@@ -218,6 +238,8 @@ int fs_create(const fs_pedigree *ped, const fs_params *params, int device, fs_en
     e->bn_rc = build_bn_plan(e->ped, e->bn.plan, e->bn_err);
     e->mcmc.C = C;
     e->mcmc_rc = build_mcmc_plan(e->ped, e->mcmc.plan, e->mcmc_err);
+    if (const char *env = std::getenv("FAMSEQ_MCMC_JIT")) e->jit.mode = env[0] == '0' ? 0 : (env[0] == '1' ? 1 : 2);
+    if (const char *env = std::getenv("FAMSEQ_JIT_MIN_WORK")) e->jit.min_work = std::atof(env);
 
     if (device >= 0) {
         cudaError_t crc = cudaSetDevice(device);
@@ -272,6 +294,7 @@ int fs_get_info(const fs_engine *e, fs_info *out) {
     out->mcmc_links = e->mcmc_rc == FS_OK ? e->mcmc.plan.n_links : 0;
     out->device = e->device;
     out->kernel_launches = e->launches;
+    out->jit_launches = e->jit_launches;
     return FS_OK;
 }
 
@@ -301,6 +324,27 @@ int fs_get_es_program(const fs_engine *e, uint32_t *words, int32_t capacity, int
     return FS_OK;
 }
 
+int fs_get_gibbs_kernel(const fs_engine *e, int compile, char *text, size_t capacity, size_t *text_len, size_t *cubin_bytes) {
+    if (!e) return fail(FS_E_ARG, "fs_get_gibbs_kernel: null engine");
+    if (e->mcmc_rc != FS_OK) return fail(e->mcmc_rc, e->mcmc_err);
+    const GibbsJitConfig cfg = gibbs_jit_default_config(e->mcmc);
+    std::string out, cubin, err;
+    if (compile) {
+        const int rc = gibbs_jit_build(e->mcmc, cfg, cubin, out, err);
+        if (rc != FS_OK) return fail(rc, err);
+    } else {
+        out = gibbs_jit_source(e->mcmc, cfg);
+    }
+    if (text_len) *text_len = out.size();
+    if (cubin_bytes) *cubin_bytes = cubin.size();
+    if (text && capacity) {
+        const size_t n = std::min(capacity - 1, out.size());
+        std::memcpy(text, out.data(), n);
+        text[n] = 0;
+    }
+    return FS_OK;
+}
+
 void *fs_alloc_pinned(size_t bytes) {
     void *p = nullptr;
     if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
@@ -314,6 +358,40 @@ void fs_free_pinned(void *p) {
 }
 
 double fs_last_kernel_ms(const fs_engine *e) { return e ? e->last_kernel_ms : 0.0; }
+
+// The specialised Gibbs kernel if it is ready (loads it when the worker has finished, starts the worker when this
+// batch is big enough); nullptr means: use the table-driven kernel for this batch.
+static int gibbs_jit_poll(fs_engine *e, double work, GibbsJitKernel **out) {
+    GibbsJitState &J = e->jit;
+    *out = nullptr;
+    if (J.mode == 0) return FS_OK;
+    int st = J.state.load(std::memory_order_acquire);
+    if (st == GibbsJitState::IDLE && (J.mode == 1 || work >= J.min_work)) {
+        J.cfg = gibbs_jit_default_config(e->mcmc);
+        J.state.store(GibbsJitState::COMPILING, std::memory_order_release);
+        auto build = [e]() {
+            GibbsJitState &j = e->jit;
+            const int rc = gibbs_jit_build(e->mcmc, j.cfg, j.cubin, j.log, j.err);
+            j.state.store(rc == FS_OK ? GibbsJitState::COMPILED : GibbsJitState::FAILED, std::memory_order_release);
+        };
+        if (J.mode == 1)
+            build();
+        else
+            J.worker = std::thread(build);
+        st = J.state.load(std::memory_order_acquire);
+    }
+    if (st == GibbsJitState::COMPILED) {
+        if (J.worker.joinable()) J.worker.join();
+        const int rc = gibbs_jit_load(e->mcmc, J.cfg, J.cubin, &J.kernel, J.err);
+        J.cubin.clear();
+        J.cubin.shrink_to_fit();
+        st = rc == FS_OK ? GibbsJitState::LOADED : GibbsJitState::FAILED;
+        J.state.store(st, std::memory_order_release);
+    }
+    if (st == GibbsJitState::FAILED && J.mode == 1) return fail(FS_E_CUDA, "FAMSEQ_MCMC_JIT=1: " + J.err);
+    if (st == GibbsJitState::LOADED) *out = J.kernel;
+    return FS_OK;
+}
 
 // One kernel launch for `B.V` variants already on the device.
 static int dispatch(fs_engine *e, int method, const BatchPtrs &B, int32_t burn, int32_t rep, uint64_t seed,
@@ -337,7 +415,18 @@ static int dispatch(fs_engine *e, int method, const BatchPtrs &B, int32_t burn, 
     case FS_METHOD_MCMC: {
         if (e->mcmc_rc != FS_OK) return fail(e->mcmc_rc, e->mcmc_err);
         if (burn < 0 || rep <= 0) return fail(FS_E_ARG, "MCMC needs burn >= 0 and rep >= 1");
-        FS_CUDA(launch_mcmc(e->mcmc, B, e->mcmc_tb, burn, rep, seed, v_offset, e->sm_count, stream));
+        GibbsJitKernel *jk = nullptr;
+        const int rc = gibbs_jit_poll(e, (double)B.V * ((double)burn + rep) * e->ped.n, &jk);
+        if (rc != FS_OK) return rc;
+        if (jk) {
+            // the specialised kernel does autosomal chains whose weights stay in its fast range; it marks the others
+            // (chrX, denormal or huge weight sums) with status 2 for a second pass of the table-driven kernel
+            FS_CUDA(gibbs_jit_launch(jk, B, burn, rep, seed, v_offset, e->sm_count, stream));
+            FS_CUDA(launch_mcmc(e->mcmc, B, e->mcmc_tb, burn, rep, seed, v_offset, e->sm_count, stream, true));
+            e->jit_launches++;
+            e->launches++;
+        } else
+            FS_CUDA(launch_mcmc(e->mcmc, B, e->mcmc_tb, burn, rep, seed, v_offset, e->sm_count, stream));
         break;
     }
     default:

@@ -48,7 +48,8 @@ struct McmcParams {
 };
 size_t mcmc_smem_bytes(const McmcParams &P, int tb);
 int mcmc_pick_block(const McmcParams &P, size_t smem_limit, size_t smem_per_sm);
+// fixup: only variants whose status byte is 2 are processed (what the specialised kernel of gibbs_jit.cu left over).
 cudaError_t launch_mcmc(const McmcParams &P, const BatchPtrs &B, int tb, int burn, int rep, uint64_t seed,
-                        int64_t v_offset, int sm_count, cudaStream_t stream);
+                        int64_t v_offset, int sm_count, cudaStream_t stream, bool fixup = false);
 
 } // namespace famseq

@@ -88,7 +88,8 @@ __device__ __forceinline__ double fast_reciprocal(double s) {
     x = fma(x, e, x);
     e = fma(-s, x, 1.0);
     x = fma(x, e, x);
-    if (!(s > 1e-290 && s < 1e290)) x = 1.0 / s; // rare
+    // rare: not a positive normal number with exponent in [-963, 963) (integer-pipe test on the high word)
+    if (!(((unsigned)__double2hiint(s) - 0x03c00000u) < 0x78600000u)) x = 1.0 / s;
     return x;
 }
 
@@ -97,7 +98,7 @@ __device__ __forceinline__ double fast_reciprocal(double s) {
 //                  shared memory then only holds the tables and the number of chains per SM is set by registers.
 template <int TB, bool WGLOBAL>
 __global__ void __launch_bounds__(TB) mcmc_kernel(const __grid_constant__ McmcParams P, const BatchPtrs B, int burn, int rep,
-                                                  uint64_t seed, int64_t v_offset, double *__restrict__ scratch, int n_tiles) {
+                                                  uint64_t seed, int64_t v_offset, double *__restrict__ scratch, int n_tiles, int fixup) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const RunConstants &C = P.C;
     const McmcPlan &pl = P.plan;
@@ -121,6 +122,7 @@ __global__ void __launch_bounds__(TB) mcmc_kernel(const __grid_constant__ McmcPa
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t v = (int64_t)tile * TB + tid;
         if (v >= B.V) continue;
+        if (fixup && B.status[v] != 2) continue; // second pass after the specialised kernel: only what it left (status 2)
         const unsigned flag = B.flags ? B.flags[v] : 0u;
         const bool chrx = (flag >> 1) & 1u;
         const VariantPriors pr = select_priors(C, flag);
@@ -303,7 +305,7 @@ __global__ void __launch_bounds__(TB) mcmc_kernel(const __grid_constant__ McmcPa
 
 template <int TB, bool WGLOBAL>
 cudaError_t launch_tb(const McmcParams &P, const BatchPtrs &B, int burn, int rep, uint64_t seed, int64_t v_offset, int sm_count,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, bool fixup) {
     const size_t smem = WGLOBAL ? (size_t)kEntries * kCopies * sizeof(double) : mcmc_smem_bytes(P, TB);
     cudaError_t rc = cudaFuncSetAttribute(mcmc_kernel<TB, WGLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) return rc;
@@ -323,7 +325,7 @@ cudaError_t launch_tb(const McmcParams &P, const BatchPtrs &B, int burn, int rep
     double *scratch = nullptr;
     rc = cudaMallocAsync(&scratch, (size_t)grid * P.plan.n * 3 * TB * sizeof(double) * (WGLOBAL ? 2 : 1), stream);
     if (rc != cudaSuccess) return rc;
-    mcmc_kernel<TB, WGLOBAL><<<grid, TB, smem, stream>>>(P, B, burn, rep, seed, v_offset, scratch, (int)n_tiles);
+    mcmc_kernel<TB, WGLOBAL><<<grid, TB, smem, stream>>>(P, B, burn, rep, seed, v_offset, scratch, (int)n_tiles, fixup ? 1 : 0);
     rc = cudaGetLastError();
     const cudaError_t rc2 = cudaFreeAsync(scratch, stream);
     return rc != cudaSuccess ? rc : rc2;
@@ -350,21 +352,21 @@ int mcmc_pick_block(const McmcParams &P, size_t smem_limit, size_t smem_per_sm) 
 }
 
 cudaError_t launch_mcmc(const McmcParams &P, const BatchPtrs &B, int tb, int burn, int rep, uint64_t seed, int64_t v_offset,
-                        int sm_count, cudaStream_t stream) {
+                        int sm_count, cudaStream_t stream, bool fixup) {
     if (B.V <= 0) return cudaSuccess;
     // Large pedigrees: the own factors of fewer than 512 chains fit in an SM's shared memory -> keep them in L2 instead.
     bool wglobal = tb < 256;
     if (const char *env = std::getenv("FAMSEQ_MCMC_WGLOBAL")) wglobal = env[0] == '1';
-    if (wglobal) return launch_tb<256, true>(P, B, burn, rep, seed, v_offset, sm_count, stream);
+    if (wglobal) return launch_tb<256, true>(P, B, burn, rep, seed, v_offset, sm_count, stream, fixup);
     switch (tb) {
-    case 256: return launch_tb<256, false>(P, B, burn, rep, seed, v_offset, sm_count, stream);
-    case 224: return launch_tb<224, false>(P, B, burn, rep, seed, v_offset, sm_count, stream);
-    case 192: return launch_tb<192, false>(P, B, burn, rep, seed, v_offset, sm_count, stream);
-    case 160: return launch_tb<160, false>(P, B, burn, rep, seed, v_offset, sm_count, stream);
-    case 128: return launch_tb<128, false>(P, B, burn, rep, seed, v_offset, sm_count, stream);
-    case 96: return launch_tb<96, false>(P, B, burn, rep, seed, v_offset, sm_count, stream);
-    case 64: return launch_tb<64, false>(P, B, burn, rep, seed, v_offset, sm_count, stream);
-    case 32: return launch_tb<32, false>(P, B, burn, rep, seed, v_offset, sm_count, stream);
+    case 256: return launch_tb<256, false>(P, B, burn, rep, seed, v_offset, sm_count, stream, fixup);
+    case 224: return launch_tb<224, false>(P, B, burn, rep, seed, v_offset, sm_count, stream, fixup);
+    case 192: return launch_tb<192, false>(P, B, burn, rep, seed, v_offset, sm_count, stream, fixup);
+    case 160: return launch_tb<160, false>(P, B, burn, rep, seed, v_offset, sm_count, stream, fixup);
+    case 128: return launch_tb<128, false>(P, B, burn, rep, seed, v_offset, sm_count, stream, fixup);
+    case 96: return launch_tb<96, false>(P, B, burn, rep, seed, v_offset, sm_count, stream, fixup);
+    case 64: return launch_tb<64, false>(P, B, burn, rep, seed, v_offset, sm_count, stream, fixup);
+    case 32: return launch_tb<32, false>(P, B, burn, rep, seed, v_offset, sm_count, stream, fixup);
     default: return cudaErrorInvalidValue;
     }
 }

@@ -59,7 +59,8 @@ class Params(ctypes.Structure):
 
 class _Info(ctypes.Structure):
     _fields_ = [(k, ctypes.c_int32) for k in ("n", "s", "n_founders", "has_loop", "es_ops", "es_slots", "bn_levels",
-                                               "bn_group", "mcmc_links", "device")] + [("kernel_launches", ctypes.c_int64)]
+                                               "bn_group", "mcmc_links", "device")] + [("kernel_launches", ctypes.c_int64),
+                                                                                      ("jit_launches", ctypes.c_int64)]
 
 
 _lib = None
@@ -106,7 +107,7 @@ def lib() -> ctypes.CDLL:
 
 EXPORTED_SYMBOLS = ["fs_default_params", "fs_device_count", "fs_create", "fs_destroy", "fs_last_error", "fs_run",
                     "fs_run_device", "fs_get_info", "fs_get_tables", "fs_alloc_pinned", "fs_free_pinned",
-                    "fs_last_kernel_ms", "fs_bench_fp64_tflops", "fs_get_es_program"]
+                    "fs_last_kernel_ms", "fs_bench_fp64_tflops", "fs_get_es_program", "fs_get_gibbs_kernel"]
 
 
 def _check(rc: int) -> None:
@@ -183,6 +184,18 @@ class Engine:
         words = np.zeros(n_words.value, np.uint32)
         _check(lib().fs_get_es_program(self._h, _ptr(words), n_words.value, None, None))
         return words, int(n_slots.value)
+
+    def gibbs_kernel(self, compile: bool = False):
+        """(text, cubin_bytes): the CUDA C++ the engine generates for this pedigree's Gibbs sampler, or, with
+        compile=True, the NVRTC/ptxas log of compiling it for sm_100a (no device needed) and the cubin size."""
+        n, cb = ctypes.c_size_t(0), ctypes.c_size_t(0)
+        f = lib().fs_get_gibbs_kernel
+        f.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t),
+                      ctypes.POINTER(ctypes.c_size_t)]
+        f.restype = ctypes.c_int
+        buf = ctypes.create_string_buffer(4 << 20)
+        _check(f(self._h, 1 if compile else 0, buf, len(buf), ctypes.byref(n), ctypes.byref(cb)))
+        return buf.value.decode("utf-8", "replace"), int(cb.value)
 
     def last_kernel_ms(self) -> float:
         return float(lib().fs_last_kernel_ms(self._h))

@@ -124,6 +124,7 @@ typedef struct fs_info {
     int32_t mcmc_links;       /* parent-child links visited per Gibbs sweep                           */
     int32_t device;           /* CUDA device or -1                                                    */
     int64_t kernel_launches;  /* kernels launched by this engine so far                               */
+    int64_t jit_launches;     /* ... of which launches of the run-time compiled Gibbs kernel          */
 } fs_info;
 int fs_get_info(const fs_engine *e, fs_info *out);
 
@@ -136,6 +137,14 @@ int fs_get_tables(const fs_engine *e, double *pcp2, double *pcp2_xf, double *pcp
  * `words` (capacity in words); *n_words / *n_slots receive its length and scratch size.  Introspection only:
  * tests interpret it on the CPU to check the pedigree compiler without a GPU.  FS_E_LOOP on looped pedigrees. */
 int fs_get_es_program(const fs_engine *e, uint32_t *words, int32_t capacity, int32_t *n_words, int32_t *n_slots);
+
+/* The Gibbs sampler of large MCMC batches is a kernel the engine writes for this one pedigree and compiles for
+ * sm_100a at run time (NVRTC; csrc/cuda/gibbs_jit.cu) -- it replaces the same reference functions as the table-driven
+ * kernel, family::calPostProbMCMC / estGenoProb (src/family.cpp:1932-2299), and returns the same bytes.  Introspection:
+ * compile == 0 copies the generated CUDA C++ into `text`; compile != 0 also compiles it (no device needed) and copies
+ * the compiler log (ptxas -v: registers, spills) instead, with the cubin size in *cubin_bytes.  `text` is
+ * NUL-terminated and truncated to `capacity`; *text_len receives the full length. */
+int fs_get_gibbs_kernel(const fs_engine *e, int compile, char *text, size_t capacity, size_t *text_len, size_t *cubin_bytes);
 
 /* Pinned host memory helpers for callers without their own CUDA runtime binding. */
 void *fs_alloc_pinned(size_t bytes);

@@ -119,3 +119,19 @@ def test_synthetic_generator_is_sliceable():
     part, pf = synth.synth_likelihoods(ped, 1000, seed=3, v0=65000, x_fraction=0.1)
     assert np.array_equal(full[65000:66000], part) and np.array_equal(ff[65000:66000], pf)
     assert full.min() > 0 and full.max() == 1.0
+
+
+@pytest.mark.parametrize("name", ["trio", "ped14", "ped40"])
+def test_generated_gibbs_kernel_compiles_for_sm_100a(name):
+    """The pedigree-specialised Gibbs kernel (csrc/cuda/gibbs_jit.cu): the engine writes CUDA C++ for the pedigree and
+    NVRTC compiles it to an sm_100a cubin; neither step needs a device.  Every member must appear as a straight-line
+    block, and the hot loop must not spill more than a few registers."""
+    ped = synth.PEDIGREES[name]()
+    with fs.Engine(ped.ids, ped.mids, ped.fids, ped.genders, ped.sequenced_cols(), device=-1) as e:
+        src, _ = e.gibbs_kernel()
+        assert src.count("// member ") == 2 * ped.n  # burn-in and sampling copies of the sweep
+        assert 'extern "C" __global__' in src and "famseq_gibbs" in src
+        log, cubin_bytes = e.gibbs_kernel(compile=True)
+    assert cubin_bytes > 0
+    m = re.search(r"(\d+) bytes spill stores", log)
+    assert m and int(m.group(1)) <= 256, log

@@ -182,6 +182,50 @@ def test_mcmc_same_stream_as_oracle(pedname, V, burn, rep):
     assert np.array_equal(half.post, got.post[V // 2:]) and np.array_equal(half.gt, got.gt[V // 2:])
 
 
+@pytest.mark.parametrize("pedname,cols,V,burn,rep", [("trio", None, 700, 20, 300), ("half_sibs", None, 500, 20, 200),
+                                                     ("three_wives", None, 300, 10, 100), ("ped14", [13, 2, 7, 0, 10, 5], 300, 10, 100),
+                                                     ("ped40", None, 600, 10, 150)])
+def test_mcmc_specialised_kernel_returns_the_same_bytes(pedname, cols, V, burn, rep, monkeypatch):
+    """The Gibbs kernel the engine generates and compiles for one pedigree (gibbs_jit.cu) against the table-driven
+    kernel: same Philox stream, same operation order, hence identical bytes -- autosomes and chrX, Known or not,
+    partially sequenced pedigrees, -LRC gating and the oracle on top."""
+    ped = synth.PEDIGREES[pedname]()
+    cols = ped.sequenced_cols() if cols is None else cols
+    lk, fl = synth.synth_likelihoods(synth._mk([(i, 0, 0, 1) for i in range(1, len(cols) + 1)]), V, seed=77, x_fraction=0.3)
+    lk[::7] = np.round(lk[::7])  # some fully certain variants: the LRC gate takes the individual-only branch
+    monkeypatch.setenv("FAMSEQ_MCMC_JIT", "0")
+    with engine_for(ped, cols) as e:
+        generic = e.run(fs.MCMC, lk, fl, burn=burn, rep=rep, seed=99, v_offset=5)
+        assert e.info()["jit_launches"] == 0
+    monkeypatch.setenv("FAMSEQ_MCMC_JIT", "1")
+    with engine_for(ped, cols) as e:
+        jit = e.run(fs.MCMC, lk, fl, burn=burn, rep=rep, seed=99, v_offset=5)
+        assert e.info()["jit_launches"] >= 1
+    assert np.array_equal(jit.status, generic.status) and np.array_equal(jit.gt, generic.gt)
+    assert np.array_equal(jit.single, generic.single, equal_nan=True)
+    assert np.array_equal(jit.post, generic.post, equal_nan=True)
+    want = O.run(ped, cols, lk, fl, method=O.MCMC, burn=burn, rep=rep, rng=O.RNG_PHILOX, seed=99, v_offset=5)
+    assert_parity(jit, want, 1e-9, f"mcmc-jit/{pedname}")
+
+
+def test_mcmc_background_compile_switches_kernels_without_changing_results(monkeypatch):
+    """Default mode: a large batch starts the compile on a worker thread, batches run on the table-driven kernel until
+    the cubin is ready, later ones on the specialised kernel; the bytes do not depend on which kernel ran."""
+    import time
+    ped = synth.half_sibs()
+    lk, fl = synth.synth_likelihoods(ped, 4000, seed=5, x_fraction=0.2)
+    monkeypatch.delenv("FAMSEQ_MCMC_JIT", raising=False)
+    monkeypatch.setenv("FAMSEQ_JIT_MIN_WORK", "1e6")
+    with engine_for(ped) as e:
+        first = e.run(fs.MCMC, lk, fl, burn=10, rep=100, seed=3)
+        deadline = time.time() + 120
+        while e.info()["jit_launches"] == 0 and time.time() < deadline:
+            time.sleep(0.5)
+            again = e.run(fs.MCMC, lk, fl, burn=10, rep=100, seed=3)
+        assert e.info()["jit_launches"] >= 1, "the specialised kernel never became ready"
+    assert np.array_equal(first.post, again.post, equal_nan=True) and np.array_equal(first.gt, again.gt)
+
+
 def test_mcmc_converges_to_exact_bn():
     """Monte-Carlo check against the exact posterior on a pedigree where the chain mixes (mu = 0.02)."""
     ped = synth.half_sibs()
