@@ -55,7 +55,8 @@ struct DeviceChunk {
 struct GibbsJitState {
     enum { IDLE, COMPILING, COMPILED, FAILED, LOADED };
     int mode = 2;
-    double min_work = 1e9; // Gibbs steps (variants x sweeps x members) in one batch before a compile is started
+    double min_work = 2e10; // Gibbs steps (variants x sweeps x members) seen by this engine before a compile is started
+    double work_seen = 0;
     std::thread worker;
     std::atomic<int> state{IDLE};
     GibbsJitConfig cfg;
@@ -366,7 +367,8 @@ static int gibbs_jit_poll(fs_engine *e, double work, GibbsJitKernel **out) {
     *out = nullptr;
     if (J.mode == 0) return FS_OK;
     int st = J.state.load(std::memory_order_acquire);
-    if (st == GibbsJitState::IDLE && (J.mode == 1 || work >= J.min_work)) {
+    J.work_seen += work;
+    if (st == GibbsJitState::IDLE && (J.mode == 1 || J.work_seen >= J.min_work)) {
         J.cfg = gibbs_jit_default_config(e->mcmc);
         J.state.store(GibbsJitState::COMPILING, std::memory_order_release);
         auto build = [e]() {

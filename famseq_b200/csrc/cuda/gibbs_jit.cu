@@ -4,15 +4,22 @@
 // table-driven kernel of mcmc_kernel.cu spends ~220 instructions per Gibbs step, most of them decoding the pedigree
 // (descriptor words, dynamic 2-bit genotype fields, padded child loops), and it keeps its 48 N bytes of chain state in
 // global memory, which makes it HBM-bound (profiles/r1i).  Here the pedigree is known when the code is written:
-//   * every member is a straight-line block; parents, children and spouses are named registers, the sex and founder
-//     cases are resolved at generation time, there is no descriptor and no loop over members or children;
-//   * a genotype is kept as the byte offset of its table row (g * 128), so a transmission look-up is one or two
-//     integer multiply-adds and three LDS.64 with immediate offsets;
-//   * the Rao-Blackwell accumulators live in shared memory (thread-private columns) and, for the first members, in
-//     registers; the own factors (1e6 * prior * lk) are read one member ahead from a block-private scratch that stays
-//     in L2 because nothing else competes for it: the sweep loop causes no DRAM traffic.
+//   * a sweep is ONE basic block of ~50 instructions per member: parents, children and spouses are named registers,
+//     sex and founder cases are resolved at generation time, there is no descriptor, no loop over members or
+//     children and no branch, so ptxas interleaves the Philox rounds, the table look-ups and the FP64 chains of
+//     neighbouring members;
+//   * a genotype is kept as the byte offset of its table row (g * 128): a transmission look-up is one integer
+//     multiply-add and three LDS.64 with immediate offsets; consecutive full sibs share the look-up of their row;
+//   * per chain, 3 own factors (1e6 * prior * lk) and 3 Rao-Blackwell accumulators per member are placed in registers,
+//     in thread-private shared-memory columns, or in a block-private scratch that stays in L2 (own factors through a
+//     software prefetch queue, accumulators through red.global.add.f64); gibbs_jit_default_config() has the measured
+//     trade-offs.  The sweep loop causes no DRAM traffic.
+// The straight-line code covers what a sweep almost always is: an autosomal variant whose weight sums are positive
+// normal numbers.  ChrX variants and chains in which a sum leaves that range are marked (status 2) and redone by the
+// table-driven kernel, which the engine launches right behind this one (engine.cu) -- so nothing is approximated.
 // The arithmetic is written with explicit round-to-nearest intrinsics in the order of mcmc_kernel.cu, and the Philox
-// counters are the same, so both kernels return the same bytes (tests/test_parity_gpu.py checks it).
+// counters are the same: both kernels return the same bytes (tests/test_parity_gpu.py checks it), which is what makes
+// it safe to compile in the background and switch kernels in the middle of a run.
 #include <dlfcn.h>
 #include <nvrtc.h>
 
@@ -137,29 +144,36 @@ struct Layout {
     int depth = 1;            // prefetch distance, in such members
 };
 
+// Members that go to the scratch are spread evenly over the sweep (so that a short prefetch queue covers the L2
+// latency and the reductions do not bunch up); of the others, the first n_reg sit in registers, the rest in shared memory.
+std::vector<Place> spread(int n, int n_reg, int n_smem) {
+    std::vector<Place> place(n, SMEM);
+    const int n_glob = std::max(0, n - n_reg - n_smem);
+    for (int i = 0; i < n; i++)
+        if ((long)(i + 1) * n_glob / n != (long)i * n_glob / n) place[i] = GLOB;
+    int left = n_reg;
+    for (int i = 0; i < n && left > 0; i++)
+        if (place[i] != GLOB) {
+            place[i] = REG;
+            left--;
+        }
+    return place;
+}
+
 Layout make_layout(int n, const GibbsJitConfig &cfg) {
     Layout L;
     L.n = n;
-    L.lk_place.assign(n, GLOB);
-    L.acc_place.assign(n, GLOB);
+    L.acc_place = spread(n, cfg.n_acc_reg, cfg.n_acc_smem);
+    L.lk_place = spread(n, cfg.n_lk_reg, cfg.n_lk_smem);
     L.lk_row.assign(n, -1);
     L.acc_row.assign(n, -1);
     for (int i = 0; i < n; i++) {
-        if (i < cfg.n_acc_reg)
-            L.acc_place[i] = REG;
-        else if (i < cfg.n_acc_reg + cfg.n_acc_smem) {
-            L.acc_place[i] = SMEM;
-            L.acc_row[i] = L.smem_rows++;
-        } else
-            L.acc_row[i] = L.glob_rows++;
+        if (L.acc_place[i] == SMEM) L.acc_row[i] = L.smem_rows++;
+        if (L.acc_place[i] == GLOB) L.acc_row[i] = L.glob_rows++;
     }
     for (int i = 0; i < n; i++) {
-        if (i < cfg.n_lk_reg)
-            L.lk_place[i] = REG;
-        else if (i < cfg.n_lk_reg + cfg.n_lk_smem) {
-            L.lk_place[i] = SMEM;
-            L.lk_row[i] = L.smem_rows++;
-        } else {
+        if (L.lk_place[i] == SMEM) L.lk_row[i] = L.smem_rows++;
+        if (L.lk_place[i] == GLOB) {
             L.lk_row[i] = L.glob_rows++;
             L.lk_glob.push_back(i);
         }
@@ -174,7 +188,9 @@ std::string smem_ref(int row, int g) { return "sa[" + std::to_string(row * 3 + g
 std::string glob_ref(int row, int g) { return "wg + " + std::to_string(row * 3 + g) + " * TB"; }
 
 // One Gibbs step of member i (family.cpp:2113-2178 / :2195-2295), as straight-line code.
-void emit_member(std::ostringstream &o, const std::vector<Member> &M, const Layout &L, int i, bool accumulate) {
+// `row` names three variables that hold the member's transmission row T[.][mother][father] (loaded by emit_sweep,
+// shared by consecutive full sibs).
+void emit_member(std::ostringstream &o, const std::vector<Member> &M, const Layout &L, int i, bool accumulate, const std::string &row) {
     const Member &m = M[i];
     o << "            { // member " << i << (m.founder ? " (founder" : " (child of ") ;
     if (!m.founder) o << m.mother << " x " << m.father;
@@ -192,11 +208,8 @@ void emit_member(std::ostringstream &o, const std::vector<Member> &M, const Layo
     } else {
         o << "                double w0 = W" << i << "_0, w1 = W" << i << "_1, w2 = W" << i << "_2;\n";
     }
-    if (!m.founder) { // transmission from the parents' current genotypes: entry g*9 + mother*3 + father
-        o << "                { const u32 ta = tA + o" << m.mother << " * 3u + o" << m.father << ";\n";
-        o << "                  w0 = __dmul_rn(w0, lds64(ta)); w1 = __dmul_rn(w1, lds64(ta + " << 9 * kRow
-          << ")); w2 = __dmul_rn(w2, lds64(ta + " << 18 * kRow << ")); }\n";
-    }
+    if (!m.founder) // transmission from the parents' current genotypes
+        o << "                w0 = __dmul_rn(w0, " << row << "_0); w1 = __dmul_rn(w1, " << row << "_1); w2 = __dmul_rn(w2, " << row << "_2);\n";
     for (const Member::Link &l : m.links) {
         if (m.male) // this member is the father: entry child*9 + mother*3 + g
             o << "                { const u32 ta = tA + o" << l.child << " * 9u + o" << l.other << " * 3u;\n"
@@ -232,6 +245,36 @@ void emit_member(std::ostringstream &o, const std::vector<Member> &M, const Layo
     o << "            }\n";
 }
 
+// One sweep over the members in ped order.  A non-founder's own factor needs the row T[g][mother][father], g = 0..2
+// (entry g*9 + mother*3 + father): full sibs that follow each other before either parent is updated again share one
+// look-up -- three shared-memory loads saved per sib, and shared-memory bandwidth is what bounds this kernel.
+void emit_sweep(std::ostringstream &o, const std::vector<Member> &M, const Layout &L, bool accumulate, const char *tag) {
+    const int n = (int)M.size();
+    std::vector<int> version(n, 0);
+    struct Row {
+        int mother, father, vm, vf;
+        std::string name;
+    };
+    std::vector<Row> rows;
+    for (int i = 0; i < n; i++) {
+        std::string row;
+        if (!M[i].founder) {
+            const int mo = M[i].mother, fa = M[i].father;
+            for (const Row &r : rows)
+                if (r.mother == mo && r.father == fa && r.vm == version[mo] && r.vf == version[fa]) row = r.name;
+            if (row.empty()) {
+                row = std::string("T") + tag + std::to_string(i);
+                o << "            const u32 a" << row << " = tA + o" << mo << " * 3u + o" << fa << ";\n";
+                o << "            const double " << row << "_0 = lds64(a" << row << "), " << row << "_1 = lds64(a" << row << " + " << 9 * kRow << "), "
+                  << row << "_2 = lds64(a" << row << " + " << 18 * kRow << ");\n";
+                rows.push_back({mo, fa, version[mo], version[fa], row});
+            }
+        }
+        emit_member(o, M, L, i, accumulate, row);
+        version[i]++;
+    }
+}
+
 // End of a sweep: the loads in flight belong to the first members of the next sweep; put them where it expects them.
 void emit_queue_rotation(std::ostringstream &o, const Layout &L) {
     const int G = (int)L.lk_glob.size(), D = L.depth;
@@ -249,18 +292,23 @@ void emit_queue_rotation(std::ostringstream &o, const Layout &L) {
 GibbsJitConfig gibbs_jit_default_config(const McmcParams &P) {
     const int n = P.plan.n;
     GibbsJitConfig c;
-    // Two warps per SM sub-partition: 256 chains per SM with up to 255 registers each.  About 100 registers run the step
-    // (a genotype offset per member, the Philox block, weights, addresses, the prefetch queue); the rest hold
-    // accumulators.  Shared memory (227 KB minus the tables) holds the remaining accumulators, then own factors.
+    // Two warps per SM sub-partition: 256 chains per SM, up to 255 registers each.  Measured on the 40-member pedigree
+    // (profiles/jit_sweep*.sh): registers are the only free storage -- a shared-memory row costs LDS bandwidth (the unit
+    // that bounds the kernel), an accumulator in L2 costs three reductions (the L2 sustains ~6.5e11 FP64 reductions/s
+    // per GPU), own factors in L2 cost three loads.  So: accumulators in registers as far as they go (the step itself
+    // needs ~118 + n), a sixth of the shared-memory rows for more accumulators, the rest of them for own factors, and
+    // whatever is left in L2.
     c.tb = 256;
     c.blocks = 1;
-    c.prefetch = 3;
-    const int spare_regs = std::max(0, 236 - (64 + n + 6 * c.prefetch));
+    c.prefetch = 1;
+    const int reg_rows = std::max(0, (254 - (118 + n)) / 6);
     const int smem_rows = (int)((kSmemPerBlockMax - kTabBytes) / ((size_t)24 * c.tb));
-    c.n_acc_reg = std::min(n, spare_regs / 6);
-    c.n_acc_smem = std::min(n - c.n_acc_reg, smem_rows);
-    c.n_lk_reg = std::min(n, std::max(0, spare_regs / 6 - c.n_acc_reg));
+    c.n_acc_reg = std::min(n, reg_rows);
+    c.n_lk_reg = std::min(n, reg_rows - c.n_acc_reg);
+    c.n_acc_smem = std::min(n - c.n_acc_reg, smem_rows / 6);
     c.n_lk_smem = std::min(n - c.n_lk_reg, smem_rows - c.n_acc_smem);
+    if (c.n_acc_reg == n && c.n_lk_reg == n) // small pedigree, everything in registers: more than one block per SM
+        c.blocks = std::max(1, std::min(4, 65536 / (c.tb * (70 + n + 12 * n))));
     c.tb = env_int("FAMSEQ_JIT_TB", c.tb);
     c.blocks = std::max(1, env_int("FAMSEQ_JIT_BLOCKS", c.blocks));
     c.prefetch = std::max(1, env_int("FAMSEQ_JIT_PF", c.prefetch));
@@ -402,11 +450,11 @@ std::string gibbs_jit_source(const McmcParams &P, const GibbsJitConfig &cfg) {
     }
     o << "\n        int sweep = 1;\n"
       << "        for (; sweep <= burn; sweep++) { // burn-in: no accumulation\n";
-    for (int i = 0; i < n; i++) emit_member(o, M, L, i, false);
+    emit_sweep(o, M, L, false, "b");
     emit_queue_rotation(o, L);
     o << "        }\n"
       << "        for (const int last = burn + rep; sweep <= last; sweep++) { // sampling sweeps, Rao-Blackwellised (family.cpp:2175-2178)\n";
-    for (int i = 0; i < n; i++) emit_member(o, M, L, i, true);
+    emit_sweep(o, M, L, true, "s");
     emit_queue_rotation(o, L);
     o << "        }\n"
       << "        if (worst >= 0x78600000u) { status[v] = 2; continue; } // a sum left the fast range: redo with the table-driven kernel\n\n"
