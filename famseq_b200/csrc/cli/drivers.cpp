@@ -6,6 +6,7 @@
 // then printed in input order.  Likelihood decoding (pow, exp) and Phred encoding (log10) stay on the
 // host with libm so that the engine sees bit-identical inputs ("hard parts").
 #include "drivers.hpp"
+#include "format_g.hpp"
 
 #include <algorithm>
 #include <chrono>
@@ -18,6 +19,9 @@
 #include <limits>
 #include <sstream>
 #include <string_view>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
 #include <thread>
 
 #include "../../../include/famseq_b200.h"
@@ -101,12 +105,8 @@ struct Lines {
     }
 };
 
-// ostream's default formatting of a double is printf's %g with 6 significant digits.
-void put_number(std::string &out, double v) {
-    char buf[40];
-    const int n = std::snprintf(buf, sizeof buf, "%g", v);
-    out.append(buf, (size_t)n);
-}
+// ostream's default formatting of a double is printf's %g with 6 significant digits (format_g.hpp: same bytes, faster).
+void put_number(std::string &out, double v) { famseq::append_g(out, v); }
 
 // file.cpp:702-749: -10*log10(p); +inf is printed as 99999, everything else as its absolute value
 void put_phred(std::string &out, double p) {
@@ -252,13 +252,76 @@ template <class F> void run_parallel(int n, F f) {
     for (auto &th : pool) th.join();
 }
 
+// Output file writer on its own thread: formatted blocks are queued in order and written while the next block is
+// being parsed, computed and formatted.  The queue is bounded (the producer waits when the disk is slower).
+class AsyncWriter {
+  public:
+    explicit AsyncWriter(FILE *f) : f_(f), th_([this] { loop(); }) {}
+    ~AsyncWriter() { close(); }
+    void push(std::string &&s) {
+        if (s.empty()) return;
+        std::unique_lock<std::mutex> lk(m_);
+        cv_space_.wait(lk, [this] { return q_.size() < 256; });
+        q_.push_back(std::move(s));
+        cv_data_.notify_one();
+    }
+    void close() { // drains the queue; the caller closes the FILE
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            if (done_) return;
+            done_ = true;
+        }
+        cv_data_.notify_one();
+        th_.join();
+    }
+
+  private:
+    void loop() {
+        for (;;) {
+            std::string s;
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_data_.wait(lk, [this] { return done_ || !q_.empty(); });
+                if (q_.empty()) return;
+                s = std::move(q_.front());
+                q_.pop_front();
+            }
+            cv_space_.notify_one();
+            std::fwrite(s.data(), 1, s.size(), f_);
+        }
+    }
+    FILE *f_;
+    std::mutex m_;
+    std::condition_variable cv_data_, cv_space_;
+    std::deque<std::string> q_;
+    bool done_ = false;
+    std::thread th_;
+};
+
+// fs_create (CUDA context, pedigree compilers) on its own thread, so that it overlaps the parsing of the first block.
+class EngineStart {
+  public:
+    EngineStart(Engine &e, const PedRows &ped, const ColumnMap &cm, const fs_params &prm, int device)
+        : th_([&e, &ped, &cm, &prm, device, this] { ok_ = e.create(ped, cm, prm, device); }) {}
+    ~EngineStart() { wait(); }
+    bool wait() {
+        if (th_.joinable()) th_.join();
+        return ok_;
+    }
+
+  private:
+    bool ok_ = false;
+    std::thread th_;
+};
+
 void emit_stats() {
     if (!std::getenv("FAMSEQ_STATS")) return;
     std::fprintf(stderr,
                  "{\"records\": %lld, \"computed\": %lld, \"failed\": %lld, \"batches\": %lld, \"parse_s\": %.4f, "
-                 "\"engine_s\": %.4f, \"kernel_ms\": %.3f, \"write_s\": %.4f, \"total_s\": %.4f}\n",
+                 "\"engine_s\": %.4f, \"kernel_ms\": %.3f, \"write_s\": %.4f, \"read_s\": %.4f, \"start_wait_s\": %.4f, "
+                 "\"drain_s\": %.4f, \"total_s\": %.4f}\n",
                  g_stats.records, g_stats.computed, g_stats.failed, g_stats.batches, g_stats.parse_s, g_stats.engine_s,
-                 g_stats.kernel_ms, g_stats.write_s, g_stats.total_s);
+                 g_stats.kernel_ms, g_stats.write_s, g_stats.read_s, g_stats.start_wait_s, g_stats.drain_s, g_stats.total_s);
 }
 
 } // namespace
@@ -337,11 +400,18 @@ bool run_vcf(const VcfOptions &opt, const PedRows &ped) {
     Priors pri;
     fill_params(opt, prm, pri);
 
+    std::thread warm([&opt] { fs_warmup(opt.device); }); // CUDA context creation overlaps reading the input
+    struct Joiner {
+        std::thread &t;
+        ~Joiner() { if (t.joinable()) t.join(); }
+    } warm_joiner{warm};
     std::string data;
+    const double t_read = now();
     if (!read_file(vcf_name, data)) {
         std::cout << "Cannot open " << vcf_name << std::endl;
         return false;
     }
+    g_stats.read_s = now() - t_read;
     FILE *fout = std::fopen(opt.output.c_str(), "wb");
     if (!fout) {
         std::cout << "Cannot open " << opt.output << std::endl;
@@ -444,10 +514,13 @@ bool run_vcf(const VcfOptions &opt, const PedRows &ped) {
     }
 
     Engine eng;
-    if (!eng.create(ped, cm, prm, opt.device)) {
-        std::fclose(fout);
-        return false;
-    }
+    EngineStart eng_start(eng, ped, cm, prm, opt.device); // joined before the first batch (or at the end of an empty input)
+    auto engine_ready = [&]() {
+        const double t0 = now();
+        const bool ready = eng_start.wait();
+        g_stats.start_wait_s += now() - t0;
+        return ready;
+    };
     int burn = opt.num_burn_in, rep = opt.num_rep; // file.cpp:644-656
     if (burn < 0) burn = 1000 * real_num_ind;
     if (rep < 0) rep = 20000 * real_num_ind;
@@ -588,7 +661,8 @@ bool run_vcf(const VcfOptions &opt, const PedRows &ped) {
         }
     };
 
-    std::fwrite(out.data(), 1, out.size(), fout); // header
+    AsyncWriter writer(fout);
+    writer.push(std::move(out)); // header
     out.clear();
     Lines in(data);
     std::vector<sv> block;
@@ -624,20 +698,26 @@ bool run_vcf(const VcfOptions &opt, const PedRows &ped) {
             std::memcpy(&batch.flags[P.first], P.flags.data(), P.flags.size());
         }
         g_stats.parse_s += now() - t0;
-        if (total && !batch.run(eng, opt.method, S, burn, rep, opt.seed, v_offset)) {
+        if (total && (!engine_ready() || !batch.run(eng, opt.method, S, burn, rep, opt.seed, v_offset))) {
             ok = false;
             break;
         }
         t0 = now();
         run_parallel(n_threads, [&](int t) { format_range(parts[t]); });
         for (Part &P : parts) {
-            std::fwrite(P.out.data(), 1, P.out.size(), fout);
+            writer.push(std::move(P.out));
             if (!P.warn.empty()) std::cout << P.warn << std::flush;
             g_stats.failed += P.failed;
         }
         v_offset += (long long)total;
         g_stats.computed += (long long)total;
         g_stats.write_s += now() - t0;
+    }
+    if (!engine_ready()) ok = false; // an input without records still reports a pedigree the engine rejects
+    {
+        const double t0 = now();
+        writer.close();
+        g_stats.drain_s = now() - t0;
     }
     std::fclose(fout);
     g_stats.total_s = now() - t_start;
@@ -654,6 +734,11 @@ bool run_lk(const LkOptions &opt, const PedRows &ped) {
     fs_params prm;
     Priors pri;
     fill_params(opt, prm, pri);
+    std::thread warm([&opt] { fs_warmup(opt.device); }); // CUDA context creation overlaps reading the input
+    struct Joiner {
+        std::thread &t;
+        ~Joiner() { if (t.joinable()) t.join(); }
+    } warm_joiner{warm};
     std::string data;
     if (!read_file(opt.lk_file, data)) {
         std::cout << "Cannot open " << opt.lk_file << std::endl;
@@ -690,10 +775,13 @@ bool run_lk(const LkOptions &opt, const PedRows &ped) {
     const int S = (int)cm.engine_cols.size();
 
     Engine eng;
-    if (!eng.create(ped, cm, prm, opt.device)) {
-        std::fclose(fout);
-        return false;
-    }
+    EngineStart eng_start(eng, ped, cm, prm, opt.device); // joined before the first batch (or at the end of an empty input)
+    auto engine_ready = [&]() {
+        const double t0 = now();
+        const bool ready = eng_start.wait();
+        g_stats.start_wait_s += now() - t0;
+        return ready;
+    };
 
     // blocks of up to kBatch rows; decoding and formatting are spread over host threads (see run_vcf)
     struct Part {
@@ -766,7 +854,8 @@ bool run_lk(const LkOptions &opt, const PedRows &ped) {
         }
     };
 
-    std::fwrite(out.data(), 1, out.size(), fout); // header
+    AsyncWriter writer(fout);
+    writer.push(std::move(out)); // header
     out.clear();
     std::vector<sv> block;
     bool eof = false;
@@ -798,20 +887,26 @@ bool run_lk(const LkOptions &opt, const PedRows &ped) {
         for (Part &P : parts)
             if (!P.lines.empty()) std::memcpy(&batch.lk[P.first * S * 3], P.lk.data(), P.lk.size() * sizeof(double));
         g_stats.parse_s += now() - t0;
-        if (total && !batch.run(eng, opt.method, S, opt.num_burn_in, opt.num_rep, opt.seed, v_offset)) {
+        if (total && (!engine_ready() || !batch.run(eng, opt.method, S, opt.num_burn_in, opt.num_rep, opt.seed, v_offset))) {
             ok = false;
             break;
         }
         t0 = now();
         run_parallel(n_threads, [&](int t) { format_range(parts[t]); });
         for (Part &P : parts) {
-            std::fwrite(P.out.data(), 1, P.out.size(), fout);
+            writer.push(std::move(P.out));
             if (!P.warn.empty()) std::cout << P.warn << std::flush;
             g_stats.failed += P.failed;
         }
         v_offset += (long long)total;
         g_stats.computed += (long long)total;
         g_stats.write_s += now() - t0;
+    }
+    if (!engine_ready()) ok = false; // an input without records still reports a pedigree the engine rejects
+    {
+        const double t0 = now();
+        writer.close();
+        g_stats.drain_s = now() - t0;
     }
     std::fclose(fout);
     g_stats.total_s = now() - t_start;

@@ -27,6 +27,7 @@ bool run_lk(const LkOptions &opt, const PedRows &ped);
 struct RunStats {
     long long records = 0, computed = 0, failed = 0, batches = 0;
     double parse_s = 0, engine_s = 0, kernel_ms = 0, write_s = 0, total_s = 0;
+    double read_s = 0, start_wait_s = 0, drain_s = 0; // input file read, waiting for fs_create, waiting for the writer
 };
 extern RunStats g_stats;
 

@@ -121,6 +121,12 @@ int fs_device_count(void) {
 
 const char *fs_last_error(void) { return g_last_error.c_str(); }
 
+int fs_warmup(int device) {
+    FS_CUDA(cudaSetDevice(device));
+    FS_CUDA(cudaFree(nullptr));
+    return FS_OK;
+}
+
 static void release_chunks(fs_engine *e) {
     for (DeviceChunk &c : e->chunk) {
         cudaFree(c.lk);

@@ -146,6 +146,10 @@ int fs_get_es_program(const fs_engine *e, uint32_t *words, int32_t capacity, int
  * NUL-terminated and truncated to `capacity`; *text_len receives the full length. */
 int fs_get_gibbs_kernel(const fs_engine *e, int compile, char *text, size_t capacity, size_t *text_len, size_t *cubin_bytes);
 
+/* Initialises the CUDA context of `device` and nothing else.  fs_create does it anyway; a caller that still has
+ * input to read can run this on a helper thread first (the command line does) and hide the ~0.3 s it takes. */
+int fs_warmup(int device);
+
 /* Pinned host memory helpers for callers without their own CUDA runtime binding. */
 void *fs_alloc_pinned(size_t bytes);
 void fs_free_pinned(void *p);

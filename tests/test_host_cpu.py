@@ -135,3 +135,12 @@ def test_generated_gibbs_kernel_compiles_for_sm_100a(name):
     assert cubin_bytes > 0
     m = re.search(r"(\d+) bytes spill stores", log)
     assert m and int(m.group(1)) <= 256, log
+
+
+def test_fast_number_formatter_matches_printf_g():
+    """The output writer's "%g" replacement (csrc/cli/format_g.hpp) against glibc's snprintf on a few million values:
+    raw bit patterns, Phred values, decimal ties and their neighbours, neighbours of powers of ten."""
+    import subprocess
+    exe = os.path.join(ROOT, "famseq_b200", "bin", "format_check")
+    r = subprocess.run([exe, "300000", "20261018"], capture_output=True, text=True)
+    assert r.returncode == 0 and "0 mismatches" in r.stdout, r.stdout + r.stderr
