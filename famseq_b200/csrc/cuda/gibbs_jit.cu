@@ -14,9 +14,10 @@
 //     in thread-private shared-memory columns, or in a block-private scratch that stays in L2 (own factors through a
 //     software prefetch queue, accumulators through red.global.add.f64); gibbs_jit_default_config() has the measured
 //     trade-offs.  The sweep loop causes no DRAM traffic.
-// The straight-line code covers what a sweep almost always is: an autosomal variant whose weight sums are positive
-// normal numbers.  ChrX variants and chains in which a sum leaves that range are marked (status 2) and redone by the
-// table-driven kernel, which the engine launches right behind this one (engine.cu) -- so nothing is approximated.
+// The kernel carries the sweep twice, with the autosomal and with the chrX rules (a thread takes the pair of loops of
+// its variant).  The straight-line code covers what a sweep almost always is: weight sums that are positive normal
+// numbers.  Chains in which a sum leaves that range are marked (status 2) and redone by the table-driven kernel,
+// which the engine launches right behind this one (engine.cu) -- so nothing is approximated.
 // The arithmetic is written with explicit round-to-nearest intrinsics in the order of mcmc_kernel.cu, and the Philox
 // counters are the same: both kernels return the same bytes (tests/test_parity_gpu.py checks it), which is what makes
 // it safe to compile in the background and switch kernels in the middle of a run.
@@ -39,7 +40,7 @@ namespace {
 
 constexpr int kCopies = 16;            // replicas of every table entry (bank spreading, as in mcmc_kernel.cu)
 constexpr int kRow = kCopies * 8;      // bytes between consecutive table entries
-constexpr int kTabBytes = 27 * kRow;   // autosomal transmission table
+constexpr int kTabBytes = 81 * kRow;   // autosome, X daughter, X son
 constexpr size_t kSmemPerBlockMax = 227 * 1024;
 
 int env_int(const char *name, int fallback) {
@@ -190,7 +191,12 @@ std::string glob_ref(int row, int g) { return "wg + " + std::to_string(row * 3 +
 // One Gibbs step of member i (family.cpp:2113-2178 / :2195-2295), as straight-line code.
 // `row` names three variables that hold the member's transmission row T[.][mother][father] (loaded by emit_sweep,
 // shared by consecutive full sibs).
-void emit_member(std::ostringstream &o, const std::vector<Member> &M, const Layout &L, int i, bool accumulate, const std::string &row) {
+// chrX sweeps (family.cpp:2183-2297): a member's own transmission comes from the table of its sex, a child's from the
+// table of the child's sex, and only males get the children factor.
+const char *table_of(bool chrx, bool male) { return chrx ? (male ? "tXM" : "tXF") : "tA"; }
+
+void emit_member(std::ostringstream &o, const std::vector<Member> &M, const Layout &L, int i, bool accumulate, const std::string &row,
+                 bool chrx) {
     const Member &m = M[i];
     o << "            { // member " << i << (m.founder ? " (founder" : " (child of ") ;
     if (!m.founder) o << m.mother << " x " << m.father;
@@ -211,12 +217,14 @@ void emit_member(std::ostringstream &o, const std::vector<Member> &M, const Layo
     if (!m.founder) // transmission from the parents' current genotypes
         o << "                w0 = __dmul_rn(w0, " << row << "_0); w1 = __dmul_rn(w1, " << row << "_1); w2 = __dmul_rn(w2, " << row << "_2);\n";
     for (const Member::Link &l : m.links) {
+        if (chrx && !m.male) break; // family.cpp:2230-2257
+        const char *tA = table_of(chrx, l.child_male);
         if (m.male) // this member is the father: entry child*9 + mother*3 + g
-            o << "                { const u32 ta = tA + o" << l.child << " * 9u + o" << l.other << " * 3u;\n"
+            o << "                { const u32 ta = " << tA << " + o" << l.child << " * 9u + o" << l.other << " * 3u;\n"
               << "                  w0 = __dmul_rn(w0, lds64(ta)); w1 = __dmul_rn(w1, lds64(ta + " << kRow
               << ")); w2 = __dmul_rn(w2, lds64(ta + " << 2 * kRow << ")); }\n";
         else // this member is the mother: entry child*9 + g*3 + father
-            o << "                { const u32 ta = tA + o" << l.child << " * 9u + o" << l.other << ";\n"
+            o << "                { const u32 ta = " << tA << " + o" << l.child << " * 9u + o" << l.other << ";\n"
               << "                  w0 = __dmul_rn(w0, lds64(ta)); w1 = __dmul_rn(w1, lds64(ta + " << 3 * kRow
               << ")); w2 = __dmul_rn(w2, lds64(ta + " << 6 * kRow << ")); }\n";
     }
@@ -248,11 +256,12 @@ void emit_member(std::ostringstream &o, const std::vector<Member> &M, const Layo
 // One sweep over the members in ped order.  A non-founder's own factor needs the row T[g][mother][father], g = 0..2
 // (entry g*9 + mother*3 + father): full sibs that follow each other before either parent is updated again share one
 // look-up -- three shared-memory loads saved per sib, and shared-memory bandwidth is what bounds this kernel.
-void emit_sweep(std::ostringstream &o, const std::vector<Member> &M, const Layout &L, bool accumulate, const char *tag) {
+void emit_sweep(std::ostringstream &o, const std::vector<Member> &M, const Layout &L, bool accumulate, bool chrx, const char *tag) {
     const int n = (int)M.size();
     std::vector<int> version(n, 0);
     struct Row {
         int mother, father, vm, vf;
+        bool male;
         std::string name;
     };
     std::vector<Row> rows;
@@ -261,16 +270,17 @@ void emit_sweep(std::ostringstream &o, const std::vector<Member> &M, const Layou
         if (!M[i].founder) {
             const int mo = M[i].mother, fa = M[i].father;
             for (const Row &r : rows)
-                if (r.mother == mo && r.father == fa && r.vm == version[mo] && r.vf == version[fa]) row = r.name;
+                if (r.mother == mo && r.father == fa && r.vm == version[mo] && r.vf == version[fa] && (!chrx || r.male == M[i].male))
+                    row = r.name;
             if (row.empty()) {
                 row = std::string("T") + tag + std::to_string(i);
-                o << "            const u32 a" << row << " = tA + o" << mo << " * 3u + o" << fa << ";\n";
+                o << "            const u32 a" << row << " = " << table_of(chrx, M[i].male) << " + o" << mo << " * 3u + o" << fa << ";\n";
                 o << "            const double " << row << "_0 = lds64(a" << row << "), " << row << "_1 = lds64(a" << row << " + " << 9 * kRow << "), "
                   << row << "_2 = lds64(a" << row << " + " << 18 * kRow << ");\n";
-                rows.push_back({mo, fa, version[mo], version[fa], row});
+                rows.push_back({mo, fa, version[mo], version[fa], M[i].male, row});
             }
         }
-        emit_member(o, M, L, i, accumulate, row);
+        emit_member(o, M, L, i, accumulate, row, chrx);
         version[i]++;
     }
 }
@@ -331,8 +341,9 @@ std::string gibbs_jit_source(const McmcParams &P, const GibbsJitConfig &cfg) {
       << L.lk_glob.size() << " L2 (prefetch " << L.depth << ")\n";
     o << "#define TB " << cfg.tb << "\n#define NCOL " << S << "\n";
     o << kPrelude;
-    o << "__constant__ u64 TAB_BITS[27] = {";
-    for (int k = 0; k < 27; k++) o << (k ? ", " : "") << bits(C.tab[0][k]);
+    o << "__constant__ u64 TAB_BITS[81] = {";
+    for (int t = 0; t < 3; t++)
+        for (int k = 0; k < 27; k++) o << (t + k ? ", " : "") << bits(C.tab[t][k]);
     o << "};\n__constant__ u64 PRIOR_BITS[12] = {";
     for (int t = 0; t < 4; t++)
         for (int g = 0; g < 3; g++) o << (t + g ? ", " : "") << bits(C.prior[t][g]);
@@ -346,10 +357,10 @@ std::string gibbs_jit_source(const McmcParams &P, const GibbsJitConfig &cfg) {
       << "             double *__restrict__ single, u8 *__restrict__ gt, u8 *__restrict__ status, i64 V, int burn, int rep,\n"
       << "             u64 seed, i64 v_offset, double *scratch, int n_tiles) {\n"
       << "    extern __shared__ __align__(16) unsigned char smem_raw[];\n"
-      << "    double *s_tab = (double *)smem_raw;              // [27][" << kCopies << "]\n"
-      << "    double *s_vec = s_tab + 27 * " << kCopies << ";           // [" << L.smem_rows << " * 3][TB] thread-private columns\n"
+      << "    double *s_tab = (double *)smem_raw;              // [81][" << kCopies << "]\n"
+      << "    double *s_vec = s_tab + 81 * " << kCopies << ";           // [" << L.smem_rows << " * 3][TB] thread-private columns\n"
       << "    const int tid = threadIdx.x, lane = tid & 31;\n"
-      << "    for (int e = tid; e < 27 * " << kCopies << "; e += TB) s_tab[e] = __longlong_as_double((i64)TAB_BITS[e / " << kCopies << "]);\n"
+      << "    for (int e = tid; e < 81 * " << kCopies << "; e += TB) s_tab[e] = __longlong_as_double((i64)TAB_BITS[e / " << kCopies << "]);\n"
       << "    __syncthreads();\n"
       << "    u32 tab_addr = (u32)__cvta_generic_to_shared(s_tab) + (u32)(lane & " << (kCopies - 1) << ") * 8u;\n"
       << "    asm volatile(\"\" : \"+r\"(tab_addr) :: \"memory\"); // table reads stay below the barrier\n"
@@ -362,11 +373,11 @@ std::string gibbs_jit_source(const McmcParams &P, const GibbsJitConfig &cfg) {
       << "        const i64 v = (i64)tile * TB + tid;\n"
       << "        if (v >= V) continue;\n"
       << "        const u32 flag = flags ? flags[v] : 0u;\n"
-      << "        if (flag & 2u) { status[v] = 2; continue; } // chrX: left to the table-driven kernel (see gibbs_jit.cu)\n"
-      << "        const bool known = flag & 1u;\n"
+      << "        const bool known = flag & 1u, chrx = (flag >> 1) & 1u;\n"
       << "        const double pa0 = __longlong_as_double((i64)PRIOR_BITS[known ? 3 : 0]), pa1 = __longlong_as_double((i64)PRIOR_BITS[known ? 4 : 1]),\n"
       << "                     pa2 = __longlong_as_double((i64)PRIOR_BITS[known ? 5 : 2]);\n"
-      << "        const double pm0 = pa0, pm1 = pa1, pm2 = pa2; // autosomes: one prior vector for both sexes\n"
+      << "        const double pm0 = chrx ? __longlong_as_double((i64)PRIOR_BITS[known ? 9 : 6]) : pa0, pm1 = chrx ? __longlong_as_double((i64)PRIOR_BITS[known ? 10 : 7]) : pa1,\n"
+      << "                     pm2 = chrx ? __longlong_as_double((i64)PRIOR_BITS[known ? 11 : 8]) : pa2;\n"
       << "        const double *lkv = lk + v * (NCOL * 3);\n"
       << "        double *gp = post + v * (NCOL * 3), *gs = single + v * (NCOL * 3);\n"
       << "        u8 *gg = gt + v * NCOL;\n"
@@ -401,7 +412,8 @@ std::string gibbs_jit_source(const McmcParams &P, const GibbsJitConfig &cfg) {
       << "            status[v] = 0;\n"
       << "            continue;\n"
       << "        }\n"
-      << "        const u32 tA = tab_addr;\n"
+      << "        const u32 tA = tab_addr, tXF = tab_addr + " << 27 * kRow << "u, tXM = tab_addr + " << 54 * kRow << "u;\n"
+      << "        (void)tA; (void)tXF; (void)tXM;\n"
       << "        u32 worst = 0u;\n\n"
       << "        // chain state: own factors (1e6 * prior) * lk for founders, 1e6 * lk otherwise (family.cpp:2115-2126)\n";
     for (int i = 0; i < n; i++) {
@@ -449,14 +461,26 @@ std::string gibbs_jit_source(const McmcParams &P, const GibbsJitConfig &cfg) {
         }
     }
     o << "\n        int sweep = 1;\n"
+      << "        const int last = burn + rep;\n"
+      << "        if (!chrx) {\n"
       << "        for (; sweep <= burn; sweep++) { // burn-in: no accumulation\n";
-    emit_sweep(o, M, L, false, "b");
+    emit_sweep(o, M, L, false, false, "b");
     emit_queue_rotation(o, L);
     o << "        }\n"
-      << "        for (const int last = burn + rep; sweep <= last; sweep++) { // sampling sweeps, Rao-Blackwellised (family.cpp:2175-2178)\n";
-    emit_sweep(o, M, L, true, "s");
+      << "        for (; sweep <= last; sweep++) { // sampling sweeps, Rao-Blackwellised (family.cpp:2175-2178)\n";
+    emit_sweep(o, M, L, true, false, "s");
     emit_queue_rotation(o, L);
     o << "        }\n"
+      << "        } else { // the same two loops with the chrX rules\n"
+      << "        for (; sweep <= burn; sweep++) {\n";
+    emit_sweep(o, M, L, false, true, "xb");
+    emit_queue_rotation(o, L);
+    o << "        }\n"
+      << "        for (; sweep <= last; sweep++) {\n";
+    emit_sweep(o, M, L, true, true, "xs");
+    emit_queue_rotation(o, L);
+    o << "        }\n"
+      << "        }\n"
       << "        if (worst >= 0x78600000u) { status[v] = 2; continue; } // a sum left the fast range: redo with the table-driven kernel\n\n"
       << "        // postProb = genoFry / numRep, not renormalised; a row summing to <= 0 fails (family.cpp:2082-2092)\n"
       << "        const double nrep = (double)rep;\n";

@@ -129,7 +129,7 @@ def test_generated_gibbs_kernel_compiles_for_sm_100a(name):
     ped = synth.PEDIGREES[name]()
     with fs.Engine(ped.ids, ped.mids, ped.fids, ped.genders, ped.sequenced_cols(), device=-1) as e:
         src, _ = e.gibbs_kernel()
-        assert src.count("// member ") == 2 * ped.n  # burn-in and sampling copies of the sweep
+        assert src.count("// member ") == 4 * ped.n  # burn-in and sampling copies of the sweep, autosomal and chrX rules
         assert 'extern "C" __global__' in src and "famseq_gibbs" in src
         log, cubin_bytes = e.gibbs_kernel(compile=True)
     assert cubin_bytes > 0
