@@ -189,19 +189,42 @@ ColumnMap map_columns(const std::vector<sv> &names, size_t first, const PedRows 
     return m;
 }
 
+// The engine(s) of a run: one fs_engine per CUDA device.  With several devices every batch is cut into contiguous
+// slices, one per device, computed concurrently (variants are independent; the Gibbs sampler's streams are keyed by the
+// global variant index, so the output does not depend on the number of devices).
 struct Engine {
-    fs_engine *h = nullptr;
-    ~Engine() { fs_destroy(h); }
-    bool create(const PedRows &ped, const ColumnMap &cm, const fs_params &prm, int device) {
+    std::vector<fs_engine *> h;
+    std::vector<int> device;
+    ~Engine() {
+        for (fs_engine *e : h) fs_destroy(e);
+    }
+    static std::vector<int> resolve(const std::vector<int> &wanted, int fallback) {
+        if (wanted.empty()) return {fallback};
+        if (wanted[0] >= 0) return wanted;
+        std::vector<int> all;
+        for (int d = 0; d < std::max(1, fs_device_count()); d++) all.push_back(d);
+        return all;
+    }
+    bool create(const PedRows &ped, const ColumnMap &cm, const fs_params &prm, const std::vector<int> &devices) {
         std::vector<int32_t> id(ped.id.begin(), ped.id.end()), mo(ped.mother_id.begin(), ped.mother_id.end()),
             fa(ped.father_id.begin(), ped.father_id.end()), ge(ped.gender.begin(), ped.gender.end());
         fs_pedigree fp{(int32_t)id.size(), id.data(), mo.data(), fa.data(), ge.data(), (int32_t)cm.engine_cols.size(),
                        cm.engine_cols.data()};
-        if (fs_create(&fp, &prm, device, &h) != FS_OK) {
-            std::cout << fs_last_error() << std::endl;
-            g_engine_failed = true;
-            return false;
-        }
+        device = devices;
+        h.assign(devices.size(), nullptr);
+        std::vector<std::string> err(devices.size());
+        std::vector<std::thread> pool; // CUDA contexts are created side by side
+        for (size_t k = 0; k < devices.size(); k++)
+            pool.emplace_back([&, k] {
+                if (fs_create(&fp, &prm, devices[k], &h[k]) != FS_OK) err[k] = fs_last_error();
+            });
+        for (auto &t : pool) t.join();
+        for (const std::string &e : err)
+            if (!e.empty()) {
+                std::cout << e << std::endl;
+                g_engine_failed = true;
+                return false;
+            }
         return true;
     }
 };
@@ -224,16 +247,34 @@ struct Pending {
         gt.resize(V * S);
         status.resize(V);
         const double t0 = now();
-        const int rc = fs_run(e.h, method, (int64_t)V, lk.data(), flags.data(), burn, rep, seed, v_offset, post.data(),
-                              single.data(), gt.data(), status.data());
-        g_stats.engine_s += now() - t0;
-        g_stats.kernel_ms += fs_last_kernel_ms(e.h);
-        g_stats.batches++;
-        if (rc != FS_OK) {
-            std::cout << fs_last_error() << std::endl;
-            g_engine_failed = true;
-            return false;
+        const size_t G = e.h.size();
+        std::vector<std::string> err(G);
+        std::vector<double> kernel_ms(G, 0.0);
+        auto slice = [&](size_t g) {
+            const size_t lo = V * g / G, hi = V * (g + 1) / G;
+            if (hi == lo) return;
+            const int rc = fs_run(e.h[g], method, (int64_t)(hi - lo), lk.data() + lo * S * 3, flags.data() + lo, burn, rep, seed,
+                                  v_offset + (long long)lo, post.data() + lo * S * 3, single.data() + lo * S * 3, gt.data() + lo * S,
+                                  status.data() + lo);
+            if (rc != FS_OK) err[g] = fs_last_error();
+            kernel_ms[g] = fs_last_kernel_ms(e.h[g]);
+        };
+        if (G == 1) {
+            slice(0);
+        } else {
+            std::vector<std::thread> pool;
+            for (size_t g = 0; g < G; g++) pool.emplace_back(slice, g);
+            for (auto &t : pool) t.join();
         }
+        g_stats.engine_s += now() - t0;
+        g_stats.kernel_ms += *std::max_element(kernel_ms.begin(), kernel_ms.end());
+        g_stats.batches++;
+        for (const std::string &m : err)
+            if (!m.empty()) {
+                std::cout << m << std::endl;
+                g_engine_failed = true;
+                return false;
+            }
         return true;
     }
 };
@@ -301,8 +342,8 @@ class AsyncWriter {
 // fs_create (CUDA context, pedigree compilers) on its own thread, so that it overlaps the parsing of the first block.
 class EngineStart {
   public:
-    EngineStart(Engine &e, const PedRows &ped, const ColumnMap &cm, const fs_params &prm, int device)
-        : th_([&e, &ped, &cm, &prm, device, this] { ok_ = e.create(ped, cm, prm, device); }) {}
+    EngineStart(Engine &e, const PedRows &ped, const ColumnMap &cm, const fs_params &prm, std::vector<int> devices)
+        : th_([&e, &ped, &cm, &prm, devices, this] { ok_ = e.create(ped, cm, prm, devices); }) {}
     ~EngineStart() { wait(); }
     bool wait() {
         if (th_.joinable()) th_.join();
@@ -514,7 +555,7 @@ bool run_vcf(const VcfOptions &opt, const PedRows &ped) {
     }
 
     Engine eng;
-    EngineStart eng_start(eng, ped, cm, prm, opt.device); // joined before the first batch (or at the end of an empty input)
+    EngineStart eng_start(eng, ped, cm, prm, Engine::resolve(opt.devices, opt.device)); // joined before the first batch (or at the end of an empty input)
     auto engine_ready = [&]() {
         const double t0 = now();
         const bool ready = eng_start.wait();
@@ -775,7 +816,7 @@ bool run_lk(const LkOptions &opt, const PedRows &ped) {
     const int S = (int)cm.engine_cols.size();
 
     Engine eng;
-    EngineStart eng_start(eng, ped, cm, prm, opt.device); // joined before the first batch (or at the end of an empty input)
+    EngineStart eng_start(eng, ped, cm, prm, Engine::resolve(opt.devices, opt.device)); // joined before the first batch (or at the end of an empty input)
     auto engine_ready = [&]() {
         const double t0 = now();
         const bool ready = eng_start.wait();

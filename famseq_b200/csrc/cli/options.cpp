@@ -2,6 +2,8 @@
 // messages are the reference's (checkInput.cpp), including its inherited wording quirks.
 #include "options.hpp"
 
+#include <string>
+
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
@@ -117,8 +119,22 @@ int common_option(Scanner &sc, const std::string &opt, CommonOptions &o) {
         return 1;
     }
     // extensions
-    if (opt == "device" && sc.value_follows()) {
-        o.device = std::atoi(sc.take());
+    if (opt == "device" && sc.value_follows()) { // k, a comma-separated list, or "all" (resolved by the driver: -1)
+        const std::string v = sc.take();
+        o.devices.clear();
+        if (v == "all") {
+            o.devices.push_back(-1);
+        } else {
+            size_t pos = 0;
+            while (pos <= v.size()) {
+                const size_t comma = v.find(',', pos);
+                const std::string item = v.substr(pos, comma == std::string::npos ? std::string::npos : comma - pos);
+                if (!item.empty()) o.devices.push_back(std::atoi(item.c_str()));
+                if (comma == std::string::npos) break;
+                pos = comma + 1;
+            }
+        }
+        o.device = (o.devices.empty() || o.devices[0] < 0) ? 0 : o.devices[0];
         return 1;
     }
     if (opt == "seed" && sc.value_follows()) {

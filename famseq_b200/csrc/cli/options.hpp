@@ -19,7 +19,8 @@ struct CommonOptions {
     int num_burn_in = 0, num_rep = 0;
     double lrc = 1.0;               // -LRC
     // extensions of this implementation (absent from the reference):
-    int device = 0;                 // -device k   CUDA device
+    int device = 0;                 // -device k | a,b,c | all   CUDA device(s); a batch is split between several
+    std::vector<int> devices;       //   (filled from -device; empty = {device})
     unsigned long long seed = 1;    // -seed n     Philox key of the Gibbs sampler
 };
 

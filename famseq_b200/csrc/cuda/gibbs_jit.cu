@@ -306,12 +306,12 @@ GibbsJitConfig gibbs_jit_default_config(const McmcParams &P) {
     // (profiles/jit_sweep*.sh): registers are the only free storage -- a shared-memory row costs LDS bandwidth (the unit
     // that bounds the kernel), an accumulator in L2 costs three reductions (the L2 sustains ~6.5e11 FP64 reductions/s
     // per GPU), own factors in L2 cost three loads.  So: accumulators in registers as far as they go (the step itself
-    // needs ~118 + n), a sixth of the shared-memory rows for more accumulators, the rest of them for own factors, and
+    // needs ~124 + n), a sixth of the shared-memory rows for more accumulators, the rest of them for own factors, and
     // whatever is left in L2.
     c.tb = 256;
     c.blocks = 1;
-    c.prefetch = 1;
-    const int reg_rows = std::max(0, (254 - (118 + n)) / 6);
+    c.prefetch = 2;
+    const int reg_rows = std::max(0, (254 - (124 + n)) / 6);
     const int smem_rows = (int)((kSmemPerBlockMax - kTabBytes) / ((size_t)24 * c.tb));
     c.n_acc_reg = std::min(n, reg_rows);
     c.n_lk_reg = std::min(n, reg_rows - c.n_acc_reg);
