@@ -117,15 +117,15 @@ std::vector<Member> decode(const McmcPlan &pl) {
     std::vector<Member> m(pl.n);
     for (int i = 0; i < pl.n; i++) {
         const uint32_t d = pl.member[i];
-        m[i].mother = d & 63u;
-        m[i].father = (d >> 6) & 63u;
-        m[i].founder = (d >> 12) & 1u;
-        m[i].male = (d >> 13) & 1u;
+        m[i].mother = d & 127u;
+        m[i].father = (d >> 7) & 127u;
+        m[i].founder = (d >> 14) & 1u;
+        m[i].male = (d >> 15) & 1u;
         m[i].col = pl.col[i];
-        const int first = (d >> 14) & 0xffu, cnt = (d >> 22) & 0xffu;
+        const int first = (d >> 16) & 0xffu, cnt = d >> 24;
         for (int k = first; k < first + cnt; k++) {
             const uint32_t l = pl.link[k];
-            m[i].links.push_back({(int)(l & 63u), (int)((l >> 6) & 63u), ((l >> 12) & 1u) != 0});
+            m[i].links.push_back({(int)(l & 127u), (int)((l >> 7) & 127u), ((l >> 14) & 1u) != 0});
         }
     }
     return m;

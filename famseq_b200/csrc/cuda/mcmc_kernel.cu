@@ -67,16 +67,20 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     o3 = c3;
 }
 
-// genotype vector, 2 bits per member; the member index is warp-uniform
-struct Genotypes {
-    uint64_t lo, hi;
-    __device__ __forceinline__ int get(int i) const { return (int)(((i < 32 ? lo : hi) >> (2 * (i & 31))) & 3u); }
+// genotype vector, 2 bits per member in GW 64-bit words (GW = 2: up to 64 members, GW = 4: up to 128); the member index
+// is warp-uniform
+template <int GW> struct Genotypes {
+    uint64_t w[GW];
+    __device__ __forceinline__ uint64_t word(int i) const {
+        if (GW == 2) return i < 32 ? w[0] : w[1];
+        return i < 64 ? (i < 32 ? w[0] : w[1]) : (i < 96 ? w[2] : w[GW - 1]);
+    }
+    __device__ __forceinline__ int get(int i) const { return (int)((word(i) >> (2 * (i & 31))) & 3u); }
     __device__ __forceinline__ void set(int i, int g) {
         const uint64_t m = 3ull << (2 * (i & 31)), v = (uint64_t)g << (2 * (i & 31));
-        if (i < 32)
-            lo = (lo & ~m) | v;
-        else
-            hi = (hi & ~m) | v;
+#pragma unroll
+        for (int k = 0; k < GW; k++)
+            if ((i >> 5) == k) w[k] = (w[k] & ~m) | v;
     }
 };
 
@@ -96,7 +100,7 @@ __device__ __forceinline__ double fast_reciprocal(double s) {
 // WGLOBAL = false: own factors in shared memory (small pedigrees: every chain of a full SM fits).
 // WGLOBAL = true : own factors in the global scratch next to the accumulators, read one member ahead through L2;
 //                  shared memory then only holds the tables and the number of chains per SM is set by registers.
-template <int TB, bool WGLOBAL>
+template <int TB, bool WGLOBAL, int GW>
 __global__ void __launch_bounds__(TB) mcmc_kernel(const __grid_constant__ McmcParams P, const BatchPtrs B, int burn, int rep,
                                                   uint64_t seed, int64_t v_offset, double *__restrict__ scratch, int n_tiles, int fixup) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -173,7 +177,7 @@ __global__ void __launch_bounds__(TB) mcmc_kernel(const __grid_constant__ McmcPa
         for (int i = 0; i < N; i++) {
             const uint32_t d = pl.member[i];
             const int col = pl.col[i];
-            const bool founder = (d >> 12) & 1u, male = (d >> 13) & 1u;
+            const bool founder = (d >> 14) & 1u, male = (d >> 15) & 1u;
 #pragma unroll
             for (int g = 0; g < 3; g++) {
                 const double lk = col >= 0 ? lkv[col * 3 + g] : 1.0;
@@ -185,7 +189,9 @@ __global__ void __launch_bounds__(TB) mcmc_kernel(const __grid_constant__ McmcPa
         const uint64_t gv = (uint64_t)(v_offset + v);
         const uint32_t gv_lo = (uint32_t)gv, gv_hi = (uint32_t)(gv >> 32);
         uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0;
-        Genotypes cur{0, 0};
+        Genotypes<GW> cur;
+#pragma unroll
+        for (int k = 0; k < GW; k++) cur.w[k] = 0;
         for (int i = 0; i < N; i++) { // family.cpp:2063-2067
             if ((i & 3) == 0) philox4x32_10(0u, (uint32_t)(i >> 2), gv_lo, gv_hi, k0, k1, r0, r1, r2, r3);
             const int q = i & 3;
@@ -208,7 +214,7 @@ __global__ void __launch_bounds__(TB) mcmc_kernel(const __grid_constant__ McmcPa
             const bool sampling = sweep > burn;
             for (int i = 0; i < N; i++) {
                 const uint32_t d = pl.member[i];
-                const bool male = (d >> 13) & 1u, founder = (d >> 12) & 1u;
+                const bool male = (d >> 15) & 1u, founder = (d >> 14) & 1u;
                 double w0, w1, w2;
                 if constexpr (WGLOBAL) {
                     w0 = nw0;
@@ -226,21 +232,21 @@ __global__ void __launch_bounds__(TB) mcmc_kernel(const __grid_constant__ McmcPa
                 }
                 const int xkind = male ? 2 * 27 : 27; // chrX table of this member / of a child, by sex
                 {   // own factor: transmission from the parents' current genotypes (a row of ones for founders)
-                    const int row = cur.get(d & 63u) * 3 + cur.get((d >> 6) & 63u);
+                    const int row = cur.get(d & 127u) * 3 + cur.get((d >> 7) & 127u);
                     const int e = founder ? kOnes : (chrx ? xkind : 0) + row;
                     const uint32_t ta = tab_addr + (uint32_t)e * (kCopies * 8u);
                     w0 *= lds64(ta);
                     w1 *= lds64(ta + 9 * kCopies * 8);
                     w2 *= lds64(ta + 18 * kCopies * 8);
                 }
-                const int lb = (d >> 14) & 0xffu;
-                const int n_links = (!chrx || male) ? (int)((d >> 22) & 0xffu) : 0; // chrX: only males get the children factor
+                const int lb = (d >> 16) & 0xffu;
+                const int n_links = (!chrx || male) ? (int)(d >> 24) : 0; // chrX: only males get the children factor
                 const uint32_t step = male ? kCopies * 8u : 3u * kCopies * 8u;     // this member sits in the father slot when male
                 auto child_entry = [&](int k) -> int {
                     const uint32_t l = pl.link[k];
-                    const int kind = chrx ? (((l >> 12) & 1u) ? 2 * 27 : 27) : 0;
-                    const int other = cur.get((l >> 6) & 63u);
-                    return kind + cur.get(l & 63u) * 9 + (male ? other * 3 : other);
+                    const int kind = chrx ? (((l >> 14) & 1u) ? 2 * 27 : 27) : 0;
+                    const int other = cur.get((l >> 7) & 127u);
+                    return kind + cur.get(l & 127u) * 9 + (male ? other * 3 : other);
                 };
                 {   // first two children in line (a row of ones when there are fewer)
                     const int e0 = n_links > 0 ? child_entry(lb) : kOnes;
@@ -303,14 +309,14 @@ __global__ void __launch_bounds__(TB) mcmc_kernel(const __grid_constant__ McmcPa
     }
 }
 
-template <int TB, bool WGLOBAL>
+template <int TB, bool WGLOBAL, int GW = 2>
 cudaError_t launch_tb(const McmcParams &P, const BatchPtrs &B, int burn, int rep, uint64_t seed, int64_t v_offset, int sm_count,
                       cudaStream_t stream, bool fixup) {
     const size_t smem = WGLOBAL ? (size_t)kEntries * kCopies * sizeof(double) : mcmc_smem_bytes(P, TB);
-    cudaError_t rc = cudaFuncSetAttribute(mcmc_kernel<TB, WGLOBAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t rc = cudaFuncSetAttribute(mcmc_kernel<TB, WGLOBAL, GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) return rc;
     int per_sm = 0;
-    rc = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mcmc_kernel<TB, WGLOBAL>, TB, smem);
+    rc = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mcmc_kernel<TB, WGLOBAL, GW>, TB, smem);
     if (rc != cudaSuccess) return rc;
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
     if (WGLOBAL) { // resident blocks per SM (measured on ped40: 1 -> 1.60e5, 2 -> 1.63e5, 3 -> 1.79e5 variants/s)
@@ -325,7 +331,7 @@ cudaError_t launch_tb(const McmcParams &P, const BatchPtrs &B, int burn, int rep
     double *scratch = nullptr;
     rc = cudaMallocAsync(&scratch, (size_t)grid * P.plan.n * 3 * TB * sizeof(double) * (WGLOBAL ? 2 : 1), stream);
     if (rc != cudaSuccess) return rc;
-    mcmc_kernel<TB, WGLOBAL><<<grid, TB, smem, stream>>>(P, B, burn, rep, seed, v_offset, scratch, (int)n_tiles, fixup ? 1 : 0);
+    mcmc_kernel<TB, WGLOBAL, GW><<<grid, TB, smem, stream>>>(P, B, burn, rep, seed, v_offset, scratch, (int)n_tiles, fixup ? 1 : 0);
     rc = cudaGetLastError();
     const cudaError_t rc2 = cudaFreeAsync(scratch, stream);
     return rc != cudaSuccess ? rc : rc2;
@@ -357,6 +363,7 @@ cudaError_t launch_mcmc(const McmcParams &P, const BatchPtrs &B, int tb, int bur
     // Large pedigrees: the own factors of fewer than 512 chains fit in an SM's shared memory -> keep them in L2 instead.
     bool wglobal = tb < 256;
     if (const char *env = std::getenv("FAMSEQ_MCMC_WGLOBAL")) wglobal = env[0] == '1';
+    if (P.plan.n > 64) return launch_tb<256, true, 4>(P, B, burn, rep, seed, v_offset, sm_count, stream, fixup); // wide genotype vector
     if (wglobal) return launch_tb<256, true>(P, B, burn, rep, seed, v_offset, sm_count, stream, fixup);
     switch (tb) {
     case 256: return launch_tb<256, false>(P, B, burn, rep, seed, v_offset, sm_count, stream, fixup);

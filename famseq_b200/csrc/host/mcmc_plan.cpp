@@ -21,11 +21,11 @@ int build_mcmc_plan(const Pedigree &ped, McmcPlan &out, std::string &err) {
                 return FS_E_TOO_LARGE;
             }
             const int other = ped.mother[c] == i ? ped.father[c] : ped.mother[c];
-            p.link[k++] = (uint16_t)(c | other << 6 | ped.male[c] << 12);
+            p.link[k++] = (uint16_t)(c | other << 7 | ped.male[c] << 14);
         }
         const bool founder = ped.founder(i);
-        p.member[i] = (uint32_t)((founder ? 0 : ped.mother[i]) | (founder ? 0 : ped.father[i]) << 6 | (founder ? 1 : 0) << 12 |
-                                 ped.male[i] << 13 | first << 14 | (k - first) << 22);
+        p.member[i] = (uint32_t)(founder ? 0 : ped.mother[i]) | (uint32_t)(founder ? 0 : ped.father[i]) << 7 | (uint32_t)(founder ? 1 : 0) << 14 |
+                      (uint32_t)ped.male[i] << 15 | (uint32_t)first << 16 | (uint32_t)(k - first) << 24;
         p.col[i] = (int16_t)ped.col_of[i];
     }
     p.n_links = k;

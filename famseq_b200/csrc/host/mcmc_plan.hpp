@@ -9,11 +9,11 @@
 
 namespace famseq {
 
-constexpr int MCMC_MAX_MEMBERS = 64; // genotype vector packed 2 bits/member in two 64-bit registers
+constexpr int MCMC_MAX_MEMBERS = 128; // genotype vector packed 2 bits/member in two (<= 64 members) or four 64-bit registers
 constexpr int MCMC_MAX_LINKS = 255;
 
-// member descriptor: bits 0-5 mother, 6-11 father, 12 founder, 13 male, 14-21 first link, 22-29 link count
-// link descriptor  : bits 0-5 child, 6-11 the child's other parent, 12 child is male
+// member descriptor: bits 0-6 mother, 7-13 father, 14 founder, 15 male, 16-23 first link, 24-31 link count
+// link descriptor  : bits 0-6 child, 7-13 the child's other parent, 14 child is male
 struct McmcPlan {
     int32_t n = 0;
     int32_t n_links = 0;

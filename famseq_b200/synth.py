@@ -128,7 +128,29 @@ def cousins_loop() -> PedFile:
     ])
 
 
-PEDIGREES = {"trio": trio, "ped14": ped14, "ped40": ped40, "half_sibs": half_sibs, "three_wives": three_wives,
+def ped100() -> PedFile:
+    """100 members, loop-free: every child of a couple marries a founder and has three children of its own, breadth first
+    (beyond the 64 members a two-register genotype vector holds; exercises the wide-vector Gibbs kernel)."""
+    rows = [(1, 0, 0, 1), (2, 0, 0, 2)]
+    couples = [(2, 1)]  # (mother id, father id)
+    nxt = 3
+    while len(rows) < 100:
+        mother, father = couples.pop(0)
+        for k in range(3):
+            if len(rows) >= 100:
+                break
+            child, sex = nxt, 1 + (nxt + k) % 2
+            rows.append((child, mother, father, sex))
+            nxt += 1
+            if len(rows) < 99:  # a founder spouse of the other sex; the pair queues up for children
+                spouse = nxt
+                rows.append((spouse, 0, 0, 3 - sex))
+                nxt += 1
+                couples.append((child, spouse) if sex == 2 else (spouse, child))
+    return _mk(rows[:100])
+
+
+PEDIGREES = {"trio": trio, "ped14": ped14, "ped40": ped40, "half_sibs": half_sibs, "three_wives": three_wives, "ped100": ped100,
              "cousins_loop": cousins_loop}
 
 

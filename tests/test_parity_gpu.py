@@ -77,6 +77,7 @@ def test_golden_mcmc_statistical(name):
     ("trio", fs.ES, 100003, 0.2), ("trio", fs.BN, 50001, 0.2), ("ped14", fs.ES, 5000, 0.2),
     ("half_sibs", fs.ES, 3000, 0.3), ("three_wives", fs.ES, 3000, 0.3), ("half_sibs", fs.BN, 40, 0.3),
     ("three_wives", fs.BN, 40, 0.3), ("cousins_loop", fs.BN, 100, 0.3), ("ped14", fs.BN, 6, 0.5),
+    ("ped100", fs.ES, 600, 0.2),
 ])
 def test_random_vs_oracle(pedname, method, V, xf):
     ped = synth.PEDIGREES[pedname]()
@@ -167,7 +168,8 @@ def test_empty_and_ragged_batches():
 # ------------------------------------------------------------------------------------------------------
 # MCMC
 # ------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("pedname,V,burn,rep", [("trio", 300, 50, 500), ("half_sibs", 100, 50, 400), ("ped40", 40, 30, 300)])
+@pytest.mark.parametrize("pedname,V,burn,rep", [("trio", 300, 50, 500), ("half_sibs", 100, 50, 400), ("ped40", 40, 30, 300),
+                                                ("ped100", 40, 20, 150)])
 def test_mcmc_same_stream_as_oracle(pedname, V, burn, rep):
     """Oracle and kernel draw from the same Philox stream: the chains visit the same states, so the
     Rao-Blackwellised posteriors agree to rounding (the kernel multiplies by 1/sum instead of dividing)."""
@@ -184,7 +186,7 @@ def test_mcmc_same_stream_as_oracle(pedname, V, burn, rep):
 
 @pytest.mark.parametrize("pedname,cols,V,burn,rep", [("trio", None, 700, 20, 300), ("half_sibs", None, 500, 20, 200),
                                                      ("three_wives", None, 300, 10, 100), ("ped14", [13, 2, 7, 0, 10, 5], 300, 10, 100),
-                                                     ("ped40", None, 600, 10, 150)])
+                                                     ("ped40", None, 600, 10, 150), ("ped100", None, 300, 10, 60)])
 def test_mcmc_specialised_kernel_returns_the_same_bytes(pedname, cols, V, burn, rep, monkeypatch):
     """The Gibbs kernel the engine generates and compiles for one pedigree (gibbs_jit.cu) against the table-driven
     kernel: same Philox stream, same operation order, hence identical bytes -- autosomes and chrX, Known or not,
