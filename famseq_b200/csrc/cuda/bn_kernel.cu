@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(256, 2) bn_kernel(const __grid_constant__ BnPa
     double *s_priv = s_bins + VPB * N * 3;                  // [R][5][nthreads]: prefix, 3 bins, pending mass of a rolled level
     double *s_red = s_priv + R * 5 * nthreads;              // [3U+1][nthreads]: unrolled bins, thread total
     double *s_single = s_red + (3 * U + 1) * nthreads;      // [VPB][S][3]
-    uint8_t *s_state = reinterpret_cast<uint8_t *>(s_single + VPB * S * 3); // [VPB] 0 enumerate, 1 single, 2 failed
+    int *s_state = reinterpret_cast<int *>(s_single + VPB * S * 3); // [VPB] bit 0: the pedigree is needed, bit 1: failed
 
     const int tid = threadIdx.x;
     const int slot = tid / G, code = tid - slot * G;
@@ -120,17 +120,20 @@ __global__ void __launch_bounds__(256, 2) bn_kernel(const __grid_constant__ BnPa
         const double *lkv = B.lk + v * S * 3;
 
         // ---- individual-only posterior + LRC gate (family.cpp:1405-1499, :767-789) ------------------
-        if (live && code == 0) {
-            bool failed = C.unseq_fail[flag & 3u] != 0;
-            bool pedigree_needed = false;
-            for (int c = 0; c < S; c++) {
+        // one input column per thread of the variant's group; the verdicts meet in s_state (bit 0: some sample wants
+        // the pedigree, bit 1: failed)
+        if (live && code == 0) s_state[slot] = C.unseq_fail[flag & 3u] != 0 ? 2 : 0;
+        __syncthreads();
+        if (live) {
+            int verdict = 0;
+            for (int c = code; c < S; c += G) {
                 const double l0 = lkv[c * 3], l1 = lkv[c * 3 + 1], l2 = lkv[c * 3 + 2];
                 const bool male = C.col_male[c] != 0;
                 const double r0 = l0 * (male ? pr.m[0] : pr.a[0]);
                 const double r1 = l1 * (male ? pr.m[1] : pr.a[1]);
                 const double r2 = l2 * (male ? pr.m[2] : pr.a[2]);
                 const double rs = __dadd_rn(__dadd_rn(r0, r1), r2);
-                if (rs <= 0.0) failed = true;
+                if (rs <= 0.0) verdict |= 2;
                 double *sg = s_single + (slot * S + c) * 3;
                 sg[0] = r0 / rs;
                 sg[1] = r1 / rs;
@@ -140,9 +143,9 @@ __global__ void __launch_bounds__(256, 2) bn_kernel(const __grid_constant__ BnPa
                 if (big < l1) big = l1;
                 if (big < l2) big = l2;
                 const double ls = __dadd_rn(__dadd_rn(l0, l1), l2);
-                if (big / ls < C.lrc) pedigree_needed = true;
+                if (big / ls < C.lrc) verdict |= 1;
             }
-            s_state[slot] = failed ? 2 : (pedigree_needed ? 0 : 1);
+            if (verdict) atomicOr(&s_state[slot], verdict);
         }
         // ---- per-variant factor tables ---------------------------------------------------------------
         if (live) { // one table row (3 factors and their sum) per thread
@@ -174,7 +177,7 @@ __global__ void __launch_bounds__(256, 2) bn_kernel(const __grid_constant__ BnPa
         double inner[3][3]; // INDEP only: split bins of the innermost level
 #pragma unroll
         for (int k = 0; k < 3; k++) inner[k][0] = inner[k][1] = inner[k][2] = 0.0;
-        if (live && s_state[slot] == 0) {
+        if (live && s_state[slot] == 1) { // pedigree needed and nothing failed
             const double *tab = s_tab + slot * TD;
             uint64_t cfg = 0;
             { // this thread's digits of the spread levels
@@ -309,42 +312,49 @@ __global__ void __launch_bounds__(256, 2) bn_kernel(const __grid_constant__ BnPa
         }
         __syncthreads();
 
-        // ---- normalise, call, write (family.cpp:943-954, :576-665) -------------------------------------
-        if (live && code == 0) {
-            const int state = s_state[slot];
-            bool failed = state == 2;
+        // ---- normalise, call, write (family.cpp:943-954, :576-665): one member / one column per thread -------------
+        const bool enumerated = live && s_state[slot] == 1;
+        if (enumerated) {
             const double *bins = s_bins + slot * N * 3;
-            if (state == 0)
-                for (int L = 0; L < N; L++) {
-                    const double sum = __dadd_rn(__dadd_rn(bins[L * 3], bins[L * 3 + 1]), bins[L * 3 + 2]);
-                    if (sum <= 0.0) failed = true;
-                }
+            bool bad = false;
+            for (int L = code; L < N; L += G)
+                if (__dadd_rn(__dadd_rn(bins[L * 3], bins[L * 3 + 1]), bins[L * 3 + 2]) <= 0.0) bad = true;
+            if (bad) atomicOr(&s_state[slot], 2);
+        }
+        __syncthreads();
+        if (live) {
+            const int state = s_state[slot];
+            const bool failed = (state & 2) != 0;
             double *gp = B.post + v * S * 3, *gs = B.single + v * S * 3;
             uint8_t *gg = B.gt + v * S;
-            if (failed) {
-                for (int k = 0; k < S * 3; k++) gp[k] = gs[k] = 0.0;
-                for (int c = 0; c < S; c++) gg[c] = 255;
-            } else {
-                const double *sg = s_single + slot * S * 3;
-                for (int k = 0; k < S * 3; k++) gs[k] = sg[k];
-                if (state == 1) {
-                    for (int k = 0; k < S * 3; k++) gp[k] = sg[k];
-                    for (int c = 0; c < S; c++) gg[c] = call_genotype(sg[c * 3], sg[c * 3 + 1], sg[c * 3 + 2]);
-                } else {
-                    for (int L = 0; L < N; L++) {
-                        const int c = pl.col[L];
-                        if (c < 0) continue;
-                        const double b0 = bins[L * 3], b1 = bins[L * 3 + 1], b2 = bins[L * 3 + 2];
-                        const double sum = __dadd_rn(__dadd_rn(b0, b1), b2);
-                        const double p0 = b0 / sum, p1 = b1 / sum, p2 = b2 / sum;
-                        gp[c * 3] = p0;
-                        gp[c * 3 + 1] = p1;
-                        gp[c * 3 + 2] = p2;
-                        gg[c] = call_genotype(p0, p1, p2);
-                    }
+            const double *sg = s_single + slot * S * 3;
+            for (int c = code; c < S; c += G) { // GPP rows, and the FPP rows when the pedigree was not used
+                const double q0 = failed ? 0.0 : sg[c * 3], q1 = failed ? 0.0 : sg[c * 3 + 1], q2 = failed ? 0.0 : sg[c * 3 + 2];
+                gs[c * 3] = q0;
+                gs[c * 3 + 1] = q1;
+                gs[c * 3 + 2] = q2;
+                if (failed || state == 0) {
+                    gp[c * 3] = q0;
+                    gp[c * 3 + 1] = q1;
+                    gp[c * 3 + 2] = q2;
+                    gg[c] = failed ? (uint8_t)255 : call_genotype(q0, q1, q2);
                 }
             }
-            B.status[v] = failed ? 1 : 0;
+            if (!failed && state == 1) {
+                const double *bins = s_bins + slot * N * 3;
+                for (int L = code; L < N; L += G) {
+                    const int c = pl.col[L];
+                    if (c < 0) continue;
+                    const double b0 = bins[L * 3], b1 = bins[L * 3 + 1], b2 = bins[L * 3 + 2];
+                    const double sum = __dadd_rn(__dadd_rn(b0, b1), b2);
+                    const double p0 = b0 / sum, p1 = b1 / sum, p2 = b2 / sum;
+                    gp[c * 3] = p0;
+                    gp[c * 3 + 1] = p1;
+                    gp[c * 3 + 2] = p2;
+                    gg[c] = call_genotype(p0, p1, p2);
+                }
+            }
+            if (code == 0) B.status[v] = failed ? 1 : 0;
         }
         __syncthreads();
     }
@@ -356,7 +366,7 @@ size_t bn_smem_bytes(const BnParams &P) {
     const BnPlan &pl = P.plan;
     size_t d = (size_t)pl.vpb * pl.table_doubles + (size_t)pl.vpb * pl.n_levels * 3 + (size_t)pl.r * 5 * pl.threads +
                (size_t)(3 * pl.u + 1) * pl.threads + (size_t)pl.vpb * P.C.s * 3;
-    return ((d * sizeof(double) + pl.vpb) + 15) & ~(size_t)15;
+    return ((d * sizeof(double) + (size_t)pl.vpb * sizeof(int)) + 15) & ~(size_t)15;
 }
 
 template <int U, bool INDEP>
