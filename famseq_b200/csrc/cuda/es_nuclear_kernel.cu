@@ -16,6 +16,9 @@
 //     (cp.async.bulk + mbarrier) and the post / single / gt / status tiles leave through TMA bulk stores, so
 //     global traffic is fully coalesced 16-byte-granular and costs no LSU wavefronts.
 // HBM-bound: 73*S+2 algorithmic bytes per variant (221 B for a trio).
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.hpp"
 
@@ -184,47 +187,18 @@ __device__ __forceinline__ bool peel(const NuclearParams &P, const VariantPriors
     return failed;
 }
 
-template <int NC, int TB>
-__global__ void __launch_bounds__(TB) es_nuclear_kernel(const __grid_constant__ NuclearParams P, const BatchPtrs B) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+// One variant: individual-only posterior, LRC gate, peeling, genotype calls -- from the thread's row of the input tile
+// into its rows of the output tiles (all in shared memory).
+template <int NC>
+__device__ __forceinline__ void variant_thread(const NuclearParams &P, const VariantPriors &pr, unsigned flag, int tid, const double *s_in,
+                                               double *s_post, double *s_single, uint8_t *s_gt, uint8_t *s_status) {
     const RunConstants &C = P.C;
     const int S = C.s, S3 = 3 * S;
-    double *s_in = reinterpret_cast<double *>(smem_raw); // [TB][S][3]
-    double *s_post = s_in + TB * S3;
-    double *s_single = s_post + TB * S3;
-    uint8_t *s_gt = reinterpret_cast<uint8_t *>(s_single + TB * S3); // [TB][S]
-    uint8_t *s_status = s_gt + ((TB * S + 15) & ~15);                 // [TB]
-    __shared__ uint64_t bar;
-
-    const int tid = threadIdx.x;
-    const int64_t v0 = (int64_t)blockIdx.x * TB;
-    const int nv = (int)min((int64_t)TB, B.V - v0);
-    const bool full = nv == TB; // full tiles go through TMA; the ragged last tile uses plain loads/stores
-    const unsigned tile_bytes = (unsigned)(TB * S3 * sizeof(double));
-
-    if (full) {
-        if (tid == 0) mbar_init(&bar, 1);
-        __syncthreads();
-        if (tid == 0) {
-            mbar_expect_tx(&bar, tile_bytes);
-            bulk_load(s_in, B.lk + v0 * S3, tile_bytes, &bar);
-        }
-    } else {
-        for (int k = tid; k < nv * S3; k += TB) s_in[k] = B.lk[v0 * S3 + k];
-    }
-    unsigned flag = 0;
-    if (tid < nv && B.flags) flag = B.flags[v0 + tid];
-    const VariantPriors pr = select_priors(C, flag);
-    if (full)
-        mbar_wait(&bar, 0);
-    else
-        __syncthreads();
-
-    if (tid < nv && P.io_probe) { // I/O ceiling probe: same tiles in and out, no arithmetic
+    if (P.io_probe) { // I/O ceiling probe: same tiles in and out, no arithmetic
         for (int k = 0; k < S3; k++) s_post[tid * S3 + k] = s_single[tid * S3 + k] = s_in[tid * S3 + k];
         for (int c = 0; c < S; c++) s_gt[tid * S + c] = 0;
         s_status[tid] = 0;
-    } else if (tid < nv) {
+    } else {
         const double *in_row = s_in + tid * S3;
         double *post_row = s_post + tid * S3;
         double *single_row = s_single + tid * S3;
@@ -262,6 +236,45 @@ __global__ void __launch_bounds__(TB) es_nuclear_kernel(const __grid_constant__ 
             s_gt[tid * S + c] = failed ? (uint8_t)255 : call_genotype(post_row[c * 3], post_row[c * 3 + 1], post_row[c * 3 + 2]);
         s_status[tid] = failed ? 1 : 0;
     }
+}
+
+template <int NC, int TB>
+__global__ void __launch_bounds__(TB) es_nuclear_kernel(const __grid_constant__ NuclearParams P, const BatchPtrs B) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const RunConstants &C = P.C;
+    const int S = C.s, S3 = 3 * S;
+    double *s_in = reinterpret_cast<double *>(smem_raw); // [TB][S][3]
+    double *s_post = s_in + TB * S3;
+    double *s_single = s_post + TB * S3;
+    uint8_t *s_gt = reinterpret_cast<uint8_t *>(s_single + TB * S3); // [TB][S]
+    uint8_t *s_status = s_gt + ((TB * S + 15) & ~15);                 // [TB]
+    __shared__ uint64_t bar;
+
+    const int tid = threadIdx.x;
+    const int64_t v0 = (int64_t)blockIdx.x * TB;
+    const int nv = (int)min((int64_t)TB, B.V - v0);
+    const bool full = nv == TB; // full tiles go through TMA; the ragged last tile uses plain loads/stores
+    const unsigned tile_bytes = (unsigned)(TB * S3 * sizeof(double));
+
+    if (full) {
+        if (tid == 0) mbar_init(&bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(&bar, tile_bytes);
+            bulk_load(s_in, B.lk + v0 * S3, tile_bytes, &bar);
+        }
+    } else {
+        for (int k = tid; k < nv * S3; k += TB) s_in[k] = B.lk[v0 * S3 + k];
+    }
+    unsigned flag = 0;
+    if (tid < nv && B.flags) flag = B.flags[v0 + tid];
+    const VariantPriors pr = select_priors(C, flag);
+    if (full)
+        mbar_wait(&bar, 0);
+    else
+        __syncthreads();
+
+    if (tid < nv) variant_thread<NC>(P, pr, flag, tid, s_in, s_post, s_single, s_gt, s_status);
 
     if (full) {
         fence_async_smem(); // make this thread's shared-memory writes visible to the TMA engine
@@ -298,12 +311,31 @@ template <int NC, int TB> cudaError_t launch_nc(const NuclearParams &P, const Ba
 
 cudaError_t launch_es_nuclear(const NuclearParams &P, const BatchPtrs &B, cudaStream_t stream) {
     if (B.V <= 0) return cudaSuccess;
-    switch (P.n_children) {
-    case 1: return launch_nc<1, 128>(P, B, stream);
-    case 2: return launch_nc<2, 128>(P, B, stream);
-    case 3: return launch_nc<3, 128>(P, B, stream);
-    case 4: return launch_nc<4, 128>(P, B, stream);
-    case 5: return launch_nc<5, 128>(P, B, stream);
+    // Variants per block (= per TMA tile).  Measured on the trio (profiles/es_tb_check.sh), fraction of the HBM peak:
+    // 32 -> 0.946, 64 -> 0.933, 128 -> 0.904, 256 -> 0.72: many one-warp blocks per SM interleave their load / compute /
+    // store phases best.  A persistent, double-buffered variant (one block per slot looping over tiles, next tile
+    // requested before the current one is computed) was slower (0.854): its barriers serialise what the block
+    // scheduler overlaps for free.
+    static const int tb = [] {
+        const char *env = std::getenv("FAMSEQ_ES_TB");
+        return env ? std::atoi(env) : 32;
+    }();
+    switch (P.n_children * 1000 + tb) {
+    case 1032: return launch_nc<1, 32>(P, B, stream);
+    case 2032: return launch_nc<2, 32>(P, B, stream);
+    case 3032: return launch_nc<3, 32>(P, B, stream);
+    case 4032: return launch_nc<4, 32>(P, B, stream);
+    case 5032: return launch_nc<5, 32>(P, B, stream);
+    case 1064: return launch_nc<1, 64>(P, B, stream);
+    case 2064: return launch_nc<2, 64>(P, B, stream);
+    case 3064: return launch_nc<3, 64>(P, B, stream);
+    case 4064: return launch_nc<4, 64>(P, B, stream);
+    case 5064: return launch_nc<5, 64>(P, B, stream);
+    case 1128: return launch_nc<1, 128>(P, B, stream);
+    case 2128: return launch_nc<2, 128>(P, B, stream);
+    case 3128: return launch_nc<3, 128>(P, B, stream);
+    case 4128: return launch_nc<4, 128>(P, B, stream);
+    case 5128: return launch_nc<5, 128>(P, B, stream);
     default: return cudaErrorInvalidValue;
     }
 }
