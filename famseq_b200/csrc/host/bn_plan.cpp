@@ -54,6 +54,10 @@ int build_bn_plan(const Pedigree &ped, BnPlan &out, std::string &err) {
         if (u >= 1 && u <= BN_MAX_UNROLL && u <= N) p.u = u;
     }
     p.h = N - p.u < 5 ? N - p.u : 5;
+    if (const char *env = std::getenv("FAMSEQ_BN_SPREAD")) { // tuning knob: levels spread over threads (3^h threads per variant)
+        const int h = std::atoi(env);
+        if (h >= 0 && h <= 5 && h <= N - p.u) p.h = h;
+    }
     p.r = N - p.u - p.h;
     p.group = 1;
     for (int k = 0; k < p.h; k++) p.group *= 3;
