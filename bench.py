@@ -426,7 +426,22 @@ def main():
                      "roofline": {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
                                   "algorithmic_flops_per_variant": flops,
                                   "note": "algorithmic flops are the reference's 2*N*3^N; the kernel carries the joint as a prefix "
-                                          "product and executes ~4 FP64 instructions per configuration, so frac can exceed 1"}}
+                                          "product and executes ~2.5 FP64 instructions per configuration, so frac can exceed 1"}}
+        # Not the contract number: the same kernel with the opt-in closed-form sum over the innermost block of childless
+        # members (FAMSEQ_BN_FACTOR=1, bn_kernel.cu: bn_block_factored) -- 3^9 instead of 3^14 configurations visited.
+        os.environ["FAMSEQ_BN_FACTOR"] = "1"
+        try:
+            with engine(ped14) as eng:
+                ms_f, l_f, _, failed_f, keep = time_device_path(torch, dist, fs, eng, wl, rank, world, 2, 1, local_rank)
+        finally:
+            del os.environ["FAMSEQ_BN_FACTOR"]
+        del keep
+        torch.cuda.empty_cache()
+        sub["BN_leaves_summed_analytically"] = {
+            "workload": "same as BN; opt-in FAMSEQ_BN_FACTOR=1: the 3^5 configurations of the five innermost (childless) members "
+                        "are summed in closed form, 3^9 configurations are enumerated; same marginals to 1e-9",
+            "variants_per_gpu": args.bn_variants, "value": world * args.bn_variants / (ms_f * 1e-3), "unit": "variants/s",
+            "ms_per_step": ms_f, "steps": 2, "warmup": 1, "gpu_launches": l_f, "failed_variants": failed_f}
     if "mcmc" in methods:
         N, founders, burn, rep = 40, 9, 1000, 10000
         wl = Workload("mcmc", ped40, "mcmc", args.mcmc_variants, burn, rep)

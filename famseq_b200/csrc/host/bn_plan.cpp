@@ -105,6 +105,7 @@ int build_bn_plan(const Pedigree &ped, BnPlan &out, std::string &err) {
     for (int x = 0; x < p.u; x++)
         for (int y = 0; y < x; y++)
             if (p.ustride[x][y]) p.independent = 0;
+    if (const char *env = std::getenv("FAMSEQ_BN_FACTOR")) p.factor_leaves = env[0] == '1';
     if (const char *env = std::getenv("FAMSEQ_BN_GENERIC")) // tuning / test knob: force the general unrolled block
         if (env[0] == '1') p.independent = 0;
     out = p;

@@ -41,6 +41,7 @@ struct BnPlan {
     // 1 when no unrolled level is a parent of another unrolled level (all ustride are zero): the factor vectors of
     // the unrolled block then depend on outer digits only and are loaded once per block instead of once per use
     int32_t independent = 0;
+    int32_t factor_leaves = 0; // FAMSEQ_BN_FACTOR=1: sum the unrolled (childless, independent) block analytically
     // largest rolled index (0 = outermost rolled level) that is a parent of an unrolled level, -1 if none: the
     // unrolled block's table rows must be re-read only when a rolled level <= this one changes
     int32_t unrolled_dep = -1;

@@ -106,6 +106,24 @@ def test_bn_every_group_shape(sizes):
         assert_parity(got, want, REL_TOL, f"BN n={n}")
 
 
+@pytest.mark.parametrize("pedname,V", [("ped14", 8), ("half_sibs", 60), ("three_wives", 60), ("cousins_loop", 60), ("trio", 500)])
+def test_bn_with_analytically_summed_leaves(pedname, V, monkeypatch):
+    """FAMSEQ_BN_FACTOR=1: the innermost block of childless members is summed in closed form instead of being enumerated
+    (bn_kernel.cu, bn_block_factored).  Same marginals as the exhaustive enumeration and as the oracle, to 1e-9."""
+    ped = synth.PEDIGREES[pedname]()
+    lk, fl = synth.synth_likelihoods(ped, V, seed=41, x_fraction=0.3)
+    want = O.run(ped, ped.sequenced_cols(), lk, fl, method=O.BN)
+    with engine_for(ped) as e:
+        plain = e.run(fs.BN, lk, fl)
+    monkeypatch.setenv("FAMSEQ_BN_FACTOR", "1")
+    with engine_for(ped) as e:
+        got = e.run(fs.BN, lk, fl)
+    assert_parity(got, want, REL_TOL, f"BN factored/{pedname}")
+    assert np.array_equal(got.gt, plain.gt) and np.array_equal(got.status, plain.status)
+    ok = plain.status == 0
+    assert rel_err(got.post[ok], plain.post[ok]) <= REL_TOL
+
+
 def test_partial_sequencing_and_column_order():
     """Input columns in a different order than the ped rows, some members unsequenced."""
     ped = synth.ped14()
