@@ -426,7 +426,8 @@ def main():
                      "roofline": {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
                                   "algorithmic_flops_per_variant": flops,
                                   "note": "algorithmic flops are the reference's 2*N*3^N; the kernel carries the joint as a prefix "
-                                          "product and executes ~2.5 FP64 instructions per configuration, so frac can exceed 1"}}
+                                          "product and executes ~2.5 FP64 instructions per configuration, so frac can exceed 1; ncu "
+                                          "(profiles/r1q_bn_r1q.txt): FP64 pipe 71.8 % busy, top stall math-pipe throttle"}}
         # Not the contract number: the same kernel with the opt-in closed-form sum over the innermost block of childless
         # members (FAMSEQ_BN_FACTOR=1, bn_kernel.cu: bn_block_factored) -- 3^9 instead of 3^14 configurations visited.
         os.environ["FAMSEQ_BN_FACTOR"] = "1"
@@ -461,7 +462,10 @@ def main():
                        "ms_per_step": ms_m, "steps": 2, "warmup": 1, "gpu_launches": l_m, "clocks": clk_m, "failed_variants": failed_m,
                        "kernel": "famseq_gibbs (generated for the pedigree, NVRTC)" if jit_m else "mcmc_kernel (table-driven)",
                        "roofline": {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
-                                    "algorithmic_flops_per_variant": flops}}
+                                    "algorithmic_flops_per_variant": flops,
+                                    "note": "a Gibbs step has no FMAs, so the DFMA peak counts every FP64 instruction twice; ncu of the "
+                                            "generated kernel (profiles/r1q_mcmc_r1q.txt): FP64 pipe 45 %, shared-memory pipe 75 % busy "
+                                            "(transmission-table look-ups and chain state) -- the unit that bounds it"}}
     out["methods"] = sub
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) -------------------------------------------------------
