@@ -3,6 +3,7 @@
 // (one process, or one host thread) per device with the variants sharded between them.
 #include <algorithm>
 #include <atomic>
+#include <memory>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -52,15 +53,21 @@ struct DeviceChunk {
 // Pedigree-specialised Gibbs kernel (gibbs_jit.cu).  FAMSEQ_MCMC_JIT: 0 = never, 1 = compile at the first MCMC batch and
 // wait for it, unset = compile on a worker thread once a batch is large enough to be worth it and run the table-driven
 // kernel until the cubin is ready (both kernels return the same bytes, so the switch is invisible).
-struct GibbsJitState {
+// The compile job owns everything the worker touches, so an engine can be destroyed while the compiler is still
+// running (the worker is detached and the job freed when it ends).
+struct GibbsJitJob {
     enum { IDLE, COMPILING, COMPILED, FAILED, LOADED };
+    McmcParams params;
+    GibbsJitConfig cfg;
+    std::string cubin, log, err;
+    std::atomic<int> state{IDLE};
+};
+struct GibbsJitState {
     int mode = 2;
     double min_work = 2e10; // Gibbs steps (variants x sweeps x members) seen by this engine before a compile is started
     double work_seen = 0;
+    std::shared_ptr<GibbsJitJob> job;
     std::thread worker;
-    std::atomic<int> state{IDLE};
-    GibbsJitConfig cfg;
-    std::string cubin, log, err;
     GibbsJitKernel *kernel = nullptr;
 };
 } // namespace
@@ -144,7 +151,12 @@ static void release_chunks(fs_engine *e) {
 
 void fs_destroy(fs_engine *e) {
     if (!e) return;
-    if (e->jit.worker.joinable()) e->jit.worker.join();
+    if (e->jit.worker.joinable()) { // do not wait for a compile nobody will use
+        if (e->jit.job && e->jit.job->state.load(std::memory_order_acquire) == GibbsJitJob::COMPILING)
+            e->jit.worker.detach();
+        else
+            e->jit.worker.join();
+    }
     if (e->device >= 0) {
         cudaSetDevice(e->device);
         gibbs_jit_unload(e->jit.kernel);
@@ -372,32 +384,34 @@ static int gibbs_jit_poll(fs_engine *e, double work, GibbsJitKernel **out) {
     GibbsJitState &J = e->jit;
     *out = nullptr;
     if (J.mode == 0) return FS_OK;
-    int st = J.state.load(std::memory_order_acquire);
     J.work_seen += work;
-    if (st == GibbsJitState::IDLE && (J.mode == 1 || J.work_seen >= J.min_work)) {
-        J.cfg = gibbs_jit_default_config(e->mcmc);
-        J.state.store(GibbsJitState::COMPILING, std::memory_order_release);
-        auto build = [e]() {
-            GibbsJitState &j = e->jit;
-            const int rc = gibbs_jit_build(e->mcmc, j.cfg, j.cubin, j.log, j.err);
-            j.state.store(rc == FS_OK ? GibbsJitState::COMPILED : GibbsJitState::FAILED, std::memory_order_release);
+    if (!J.job && (J.mode == 1 || J.work_seen >= J.min_work)) {
+        J.job = std::make_shared<GibbsJitJob>();
+        J.job->params = e->mcmc;
+        J.job->cfg = gibbs_jit_default_config(e->mcmc);
+        J.job->state.store(GibbsJitJob::COMPILING, std::memory_order_release);
+        std::shared_ptr<GibbsJitJob> job = J.job;
+        auto build = [job]() {
+            const int rc = gibbs_jit_build(job->params, job->cfg, job->cubin, job->log, job->err);
+            job->state.store(rc == FS_OK ? GibbsJitJob::COMPILED : GibbsJitJob::FAILED, std::memory_order_release);
         };
         if (J.mode == 1)
             build();
         else
             J.worker = std::thread(build);
-        st = J.state.load(std::memory_order_acquire);
     }
-    if (st == GibbsJitState::COMPILED) {
+    if (!J.job) return FS_OK;
+    int st = J.job->state.load(std::memory_order_acquire);
+    if (st == GibbsJitJob::COMPILED) {
         if (J.worker.joinable()) J.worker.join();
-        const int rc = gibbs_jit_load(e->mcmc, J.cfg, J.cubin, &J.kernel, J.err);
-        J.cubin.clear();
-        J.cubin.shrink_to_fit();
-        st = rc == FS_OK ? GibbsJitState::LOADED : GibbsJitState::FAILED;
-        J.state.store(st, std::memory_order_release);
+        const int rc = gibbs_jit_load(e->mcmc, J.job->cfg, J.job->cubin, &J.kernel, J.job->err);
+        J.job->cubin.clear();
+        J.job->cubin.shrink_to_fit();
+        st = rc == FS_OK ? GibbsJitJob::LOADED : GibbsJitJob::FAILED;
+        J.job->state.store(st, std::memory_order_release);
     }
-    if (st == GibbsJitState::FAILED && J.mode == 1) return fail(FS_E_CUDA, "FAMSEQ_MCMC_JIT=1: " + J.err);
-    if (st == GibbsJitState::LOADED) *out = J.kernel;
+    if (st == GibbsJitJob::FAILED && J.mode == 1) return fail(FS_E_CUDA, "FAMSEQ_MCMC_JIT=1: " + J.job->err);
+    if (st == GibbsJitJob::LOADED) *out = J.kernel;
     return FS_OK;
 }
 
