@@ -398,19 +398,24 @@ def main():
 
     # ---- the other two methods ---------------------------------------------------------------------------
     sub = {}
-    if "es14" in methods:  # the general message-program interpreter (any loop-free pedigree), HBM roofline
+    if "es14" in methods:  # ES on a pedigree that is not a nuclear family (any loop-free pedigree), HBM roofline
         wl = Workload("es14", ped14, "es", args.es14_variants)
+        # the message program as generated straight-line code (csrc/cuda/es_jit.cu); compiled in the warm-up step here,
+        # on a worker thread after 2e10 variants otherwise (FAMSEQ_ES_JIT=0: the interpreter of es_kernel.cu)
+        os.environ.setdefault("FAMSEQ_ES_JIT", "1")
         with engine(ped14) as eng:
             ms_e, l_e, clk_e, failed_e, keep = time_device_path(torch, dist, fs, eng, wl, rank, world, 5, 2, local_rank)
+            jit_e = eng.info()["jit_launches"]
         del keep
         torch.cuda.empty_cache()
         ach = algorithmic_bytes(14) * args.es14_variants / (ms_e * 1e-3) / 1e9
-        sub["ES_ped14"] = {"workload": "synthetic 14-member 3-generation pedigree, ES peeling through the message-program interpreter",
+        sub["ES_ped14"] = {"workload": "synthetic 14-member 3-generation pedigree, ES peeling (compiled message program)",
+                           "kernel": "famseq_es (generated for the pedigree, NVRTC)" if jit_e else "es_kernel (message-program interpreter)",
                            "variants_per_gpu": args.es14_variants, "value": world * args.es14_variants / (ms_e * 1e-3),
                            "unit": "variants/s", "ms_per_step": ms_e, "steps": 5, "warmup": 2, "gpu_launches": l_e, "clocks": clk_e,
                            "failed_variants": failed_e,
                            "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                                        "algorithmic_bytes_per_variant": algorithmic_bytes(14), "kernel": "es_kernel<TB>"}}
+                                        "algorithmic_bytes_per_variant": algorithmic_bytes(14)}}
     if "bn" in methods:
         N = 14
         wl = Workload("bn", ped14, "bn", args.bn_variants)

@@ -16,6 +16,7 @@
 #include "../host/es_compiler.hpp"
 #include "../host/mcmc_planner.hpp"
 #include "../host/pedigree.hpp"
+#include "es_jit.hpp"
 #include "gibbs_jit.hpp"
 #include "kernels.hpp"
 
@@ -62,6 +63,22 @@ struct GibbsJitJob {
     std::string cubin, log, err;
     std::atomic<int> state{IDLE};
 };
+// The same for the generated Elston-Stewart kernel (es_jit.cu; pedigrees the nuclear-family kernel does not cover).
+// FAMSEQ_ES_JIT: 0 = never, 1 = compile at the first ES batch, unset = on a worker thread after 2e10 variants (the
+// interpreter does 1.5e9 variants/s, so only very long device-resident runs get there).
+struct EsJitJob {
+    enum { IDLE, COMPILING, COMPILED, FAILED, LOADED };
+    EsParams params;
+    std::string cubin, log, err;
+    std::atomic<int> state{IDLE};
+};
+struct EsJitState {
+    int mode = 2;
+    double min_work = 2e10, work_seen = 0;
+    std::shared_ptr<EsJitJob> job;
+    std::thread worker;
+    EsJitKernel *kernel = nullptr;
+};
 struct GibbsJitState {
     int mode = 2;
     double min_work = 2e10; // Gibbs steps (variants x sweeps x members) seen by this engine before a compile is started
@@ -97,6 +114,7 @@ struct fs_engine {
     std::string mcmc_err;
     int mcmc_tb = 0;
     GibbsJitState jit;
+    EsJitState es_jit;
 
     DeviceChunk chunk[kPipelineDepth];
     int64_t launches = 0, jit_launches = 0;
@@ -157,9 +175,16 @@ void fs_destroy(fs_engine *e) {
         else
             e->jit.worker.join();
     }
+    if (e->es_jit.worker.joinable()) {
+        if (e->es_jit.job && e->es_jit.job->state.load(std::memory_order_acquire) == EsJitJob::COMPILING)
+            e->es_jit.worker.detach();
+        else
+            e->es_jit.worker.join();
+    }
     if (e->device >= 0) {
         cudaSetDevice(e->device);
         gibbs_jit_unload(e->jit.kernel);
+        es_jit_unload(e->es_jit.kernel);
         release_chunks(e);
     }
     delete e;
@@ -259,6 +284,7 @@ int fs_create(const fs_pedigree *ped, const fs_params *params, int device, fs_en
     e->mcmc_rc = build_mcmc_plan(e->ped, e->mcmc.plan, e->mcmc_err);
     if (const char *env = std::getenv("FAMSEQ_MCMC_JIT")) e->jit.mode = env[0] == '0' ? 0 : (env[0] == '1' ? 1 : 2);
     if (const char *env = std::getenv("FAMSEQ_JIT_MIN_WORK")) e->jit.min_work = std::atof(env);
+    if (const char *env = std::getenv("FAMSEQ_ES_JIT")) e->es_jit.mode = env[0] == '0' ? 0 : (env[0] == '1' ? 1 : 2);
 
     if (device >= 0) {
         cudaError_t crc = cudaSetDevice(device);
@@ -364,6 +390,28 @@ int fs_get_gibbs_kernel(const fs_engine *e, int compile, char *text, size_t capa
     return FS_OK;
 }
 
+int fs_get_es_kernel(const fs_engine *e, int compile, char *text, size_t capacity, size_t *text_len, size_t *cubin_bytes) {
+    if (!e) return fail(FS_E_ARG, "fs_get_es_kernel: null engine");
+    if (e->es_rc != FS_OK) return fail(e->es_rc, e->es_err);
+    if (!es_jit_fits(e->es, 227 * 1024))
+        return fail(FS_E_TOO_LARGE, "pedigree too large for the generated ES kernel (the interpreter is used)");
+    std::string out, cubin, err;
+    if (compile) {
+        const int rc = es_jit_build(e->es, cubin, out, err);
+        if (rc != FS_OK) return fail(rc, err);
+    } else {
+        out = es_jit_source(e->es);
+    }
+    if (text_len) *text_len = out.size();
+    if (cubin_bytes) *cubin_bytes = cubin.size();
+    if (text && capacity) {
+        const size_t n = std::min(capacity - 1, out.size());
+        std::memcpy(text, out.data(), n);
+        text[n] = 0;
+    }
+    return FS_OK;
+}
+
 void *fs_alloc_pinned(size_t bytes) {
     void *p = nullptr;
     if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
@@ -415,6 +463,41 @@ static int gibbs_jit_poll(fs_engine *e, double work, GibbsJitKernel **out) {
     return FS_OK;
 }
 
+// The generated ES kernel if it is ready; nullptr means: use the interpreter for this batch.
+static int es_jit_poll(fs_engine *e, double variants, EsJitKernel **out) {
+    EsJitState &J = e->es_jit;
+    *out = nullptr;
+    if (J.mode == 0 || !es_jit_fits(e->es, e->smem_limit)) return FS_OK;
+    J.work_seen += variants;
+    if (!J.job && (J.mode == 1 || J.work_seen >= J.min_work)) {
+        J.job = std::make_shared<EsJitJob>();
+        J.job->params = e->es;
+        J.job->state.store(EsJitJob::COMPILING, std::memory_order_release);
+        std::shared_ptr<EsJitJob> job = J.job;
+        auto build = [job]() {
+            const int rc = es_jit_build(job->params, job->cubin, job->log, job->err);
+            job->state.store(rc == FS_OK ? EsJitJob::COMPILED : EsJitJob::FAILED, std::memory_order_release);
+        };
+        if (J.mode == 1)
+            build();
+        else
+            J.worker = std::thread(build);
+    }
+    if (!J.job) return FS_OK;
+    int st = J.job->state.load(std::memory_order_acquire);
+    if (st == EsJitJob::COMPILED) {
+        if (J.worker.joinable()) J.worker.join();
+        const int rc = es_jit_load(e->es, J.job->cubin, &J.kernel, J.job->err);
+        J.job->cubin.clear();
+        J.job->cubin.shrink_to_fit();
+        st = rc == FS_OK ? EsJitJob::LOADED : EsJitJob::FAILED;
+        J.job->state.store(st, std::memory_order_release);
+    }
+    if (st == EsJitJob::FAILED && J.mode == 1) return fail(FS_E_CUDA, "FAMSEQ_ES_JIT=1: " + J.job->err);
+    if (st == EsJitJob::LOADED) *out = J.kernel;
+    return FS_OK;
+}
+
 // One kernel launch for `B.V` variants already on the device.
 static int dispatch(fs_engine *e, int method, const BatchPtrs &B, int32_t burn, int32_t rep, uint64_t seed,
                     int64_t v_offset, cudaStream_t stream) {
@@ -423,10 +506,21 @@ static int dispatch(fs_engine *e, int method, const BatchPtrs &B, int32_t burn, 
     case FS_METHOD_ES: {
         if (e->es_rc != FS_OK) return fail(e->es_rc, e->es_err);
         const bool tma_ok = ((reinterpret_cast<uintptr_t>(B.gt) | reinterpret_cast<uintptr_t>(B.status)) & 15u) == 0;
-        if (e->is_nuclear && tma_ok && !e->force_generic_es)
+        if (e->is_nuclear && tma_ok && !e->force_generic_es) {
             FS_CUDA(launch_es_nuclear(e->nuclear, B, stream));
-        else
+            break;
+        }
+        EsJitKernel *jk = nullptr;
+        if (tma_ok && !e->force_generic_es) {
+            const int rc = es_jit_poll(e, (double)B.V, &jk);
+            if (rc != FS_OK) return rc;
+        }
+        if (jk) {
+            FS_CUDA(es_jit_launch(jk, B, stream));
+            e->jit_launches++;
+        } else {
             FS_CUDA(launch_es(e->es, B, e->es_tb, stream));
+        }
         break;
     }
     case FS_METHOD_BN: {

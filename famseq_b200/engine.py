@@ -107,7 +107,7 @@ def lib() -> ctypes.CDLL:
 
 EXPORTED_SYMBOLS = ["fs_default_params", "fs_device_count", "fs_create", "fs_destroy", "fs_last_error", "fs_run",
                     "fs_run_device", "fs_get_info", "fs_get_tables", "fs_alloc_pinned", "fs_free_pinned",
-                    "fs_last_kernel_ms", "fs_bench_fp64_tflops", "fs_get_es_program", "fs_get_gibbs_kernel", "fs_warmup"]
+                    "fs_last_kernel_ms", "fs_bench_fp64_tflops", "fs_get_es_program", "fs_get_gibbs_kernel", "fs_get_es_kernel", "fs_warmup"]
 
 
 def _check(rc: int) -> None:
@@ -184,6 +184,20 @@ class Engine:
         words = np.zeros(n_words.value, np.uint32)
         _check(lib().fs_get_es_program(self._h, _ptr(words), n_words.value, None, None))
         return words, int(n_slots.value)
+
+    def es_kernel(self, compile: bool = False):
+        """(text, cubin_bytes): the CUDA C++ generated for this pedigree's Elston-Stewart peeling, or the compile log."""
+        return self._generated("fs_get_es_kernel", compile)
+
+    def _generated(self, symbol: str, compile: bool):
+        n, cb = ctypes.c_size_t(0), ctypes.c_size_t(0)
+        f = getattr(lib(), symbol)
+        f.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t),
+                      ctypes.POINTER(ctypes.c_size_t)]
+        f.restype = ctypes.c_int
+        buf = ctypes.create_string_buffer(16 << 20)
+        _check(f(self._h, 1 if compile else 0, buf, len(buf), ctypes.byref(n), ctypes.byref(cb)))
+        return buf.value.decode("utf-8", "replace"), int(cb.value)
 
     def gibbs_kernel(self, compile: bool = False):
         """(text, cubin_bytes): the CUDA C++ the engine generates for this pedigree's Gibbs sampler, or, with

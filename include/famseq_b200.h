@@ -146,6 +146,12 @@ int fs_get_es_program(const fs_engine *e, uint32_t *words, int32_t capacity, int
  * NUL-terminated and truncated to `capacity`; *text_len receives the full length. */
 int fs_get_gibbs_kernel(const fs_engine *e, int compile, char *text, size_t capacity, size_t *text_len, size_t *cubin_bytes);
 
+/* The same for Elston-Stewart peeling of pedigrees that are not nuclear families: the message program as straight-line
+ * code (csrc/cuda/es_jit.cu), replacing family::calPostProbPeeling + calAntProb[X] + calPosProb[X]
+ * (src/family.cpp:1126-1403, :1501-1930) with the same doubles as the interpreter.  FAMSEQ_ES_JIT=1 uses it from the
+ * first batch, unset: after 2e10 variants.  FS_E_LOOP on looped pedigrees. */
+int fs_get_es_kernel(const fs_engine *e, int compile, char *text, size_t capacity, size_t *text_len, size_t *cubin_bytes);
+
 /* Initialises the CUDA context of `device` and nothing else.  fs_create does it anyway; a caller that still has
  * input to read can run this on a helper thread first (the command line does) and hide the ~0.3 s it takes. */
 int fs_warmup(int device);

@@ -144,3 +144,21 @@ def test_fast_number_formatter_matches_printf_g():
     exe = os.path.join(ROOT, "famseq_b200", "bin", "format_check")
     r = subprocess.run([exe, "300000", "20261018"], capture_output=True, text=True)
     assert r.returncode == 0 and "0 mismatches" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("name", ["half_sibs", "ped14"])
+def test_generated_es_kernel_compiles_for_sm_100a(name):
+    """The Elston-Stewart message program as straight-line code (csrc/cuda/es_jit.cu): generated and compiled with NVRTC
+    without a device; big pedigrees are refused (they stay with the interpreter)."""
+    ped = synth.PEDIGREES[name]()
+    with fs.Engine(ped.ids, ped.mids, ped.fids, ped.genders, ped.sequenced_cols(), device=-1) as e:
+        src, _ = e.es_kernel()
+        assert "peel_a(" in src and "peel_x(" in src and 'extern "C" __global__' in src
+        log, cubin_bytes = e.es_kernel(compile=True)
+    assert cubin_bytes > 0
+    m = re.search(r"(\d+) bytes spill stores", log)
+    assert m and int(m.group(1)) <= 512, log
+    big = synth.ped100()
+    with fs.Engine(big.ids, big.mids, big.fids, big.genders, big.sequenced_cols(), device=-1) as e:
+        with pytest.raises(fs.FamSeqError):
+            e.es_kernel()

@@ -124,6 +124,31 @@ def test_bn_with_analytically_summed_leaves(pedname, V, monkeypatch):
     assert rel_err(got.post[ok], plain.post[ok]) <= REL_TOL
 
 
+@pytest.mark.parametrize("pedname,cols,V", [("ped14", None, 20011), ("half_sibs", None, 5003), ("three_wives", None, 5000),
+                                          ("ped14", [13, 2, 7, 0, 10, 5], 4001)])
+def test_es_generated_kernel_returns_the_same_doubles(pedname, cols, V, monkeypatch):
+    """FAMSEQ_ES_JIT=1: the message program as straight-line code (es_jit.cu) against the interpreter (es_kernel.cu) and
+    the oracle: same doubles (autosomes, chrX, Known, failing and LRC-gated variants, a ragged last tile)."""
+    ped = synth.PEDIGREES[pedname]()
+    cols = ped.sequenced_cols() if cols is None else cols
+    lk, fl = synth.synth_likelihoods(synth._mk([(i, 0, 0, 1) for i in range(1, len(cols) + 1)]), V, seed=91, x_fraction=0.3)
+    lk[::7] = np.round(lk[::7])  # certain variants: the LRC gate keeps the pedigree out
+    lk[5::11] = 0.0              # a failing variant every now and then
+    monkeypatch.setenv("FAMSEQ_ES_JIT", "0")
+    with engine_for(ped, cols) as e:
+        interp = e.run(fs.ES, lk, fl)
+        assert e.info()["jit_launches"] == 0
+    monkeypatch.setenv("FAMSEQ_ES_JIT", "1")
+    with engine_for(ped, cols) as e:
+        got = e.run(fs.ES, lk, fl)
+        assert e.info()["jit_launches"] >= 1
+    assert np.array_equal(got.status, interp.status) and np.array_equal(got.gt, interp.gt)
+    assert np.array_equal(got.single, interp.single, equal_nan=True) and np.array_equal(got.post, interp.post, equal_nan=True)
+    want = O.run(ped, cols, lk, fl, method=O.ES)
+    ok = want["status"] == 0
+    assert np.array_equal(got.status, want["status"]) and np.array_equal(got.post[ok], want["post"][ok])
+
+
 def test_partial_sequencing_and_column_order():
     """Input columns in a different order than the ped rows, some members unsequenced."""
     ped = synth.ped14()
