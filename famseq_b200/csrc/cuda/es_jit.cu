@@ -275,7 +275,9 @@ std::string es_jit_source(const EsParams &P) {
         Emitter(P, x != 0, o).run();
         o << "    return failed;\n}\n";
     }
-    o << "\nextern \"C\" __global__ void __launch_bounds__(TB)\n"
+    int min_blocks = 0; // tuning knob: resident blocks per SM the register allocation is forced to allow
+    if (const char *env = std::getenv("FAMSEQ_ES_JIT_BLOCKS")) min_blocks = std::max(0, std::min(32, std::atoi(env)));
+    o << "\nextern \"C\" __global__ void __launch_bounds__(TB" << (min_blocks ? ", " + std::to_string(min_blocks) : std::string()) << ")\n"
       << "famseq_es(const double *__restrict__ lk, const u8 *__restrict__ flags, double *__restrict__ post, double *__restrict__ single,\n"
       << "          u8 *__restrict__ gt, u8 *__restrict__ status, i64 V) {\n"
       << "    extern __shared__ __align__(128) unsigned char smem_raw[];\n"
