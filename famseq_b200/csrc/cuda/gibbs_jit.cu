@@ -23,6 +23,7 @@
 // it safe to compile in the background and switch kernels in the middle of a run.
 #include <dlfcn.h>
 #include <nvrtc.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -33,6 +34,9 @@
 
 #include "../../../include/famseq_b200.h"
 #include "gibbs_jit.hpp"
+
+#define FS_STR2(x) #x
+#define FS_STR(x) FS_STR2(x)
 
 namespace famseq {
 
@@ -561,7 +565,43 @@ const Nvrtc &nvrtc() {
 
 } // namespace
 
+// Optional cubin cache (FAMSEQ_JIT_CACHE_DIR=<directory>): a run on a pedigree that was compiled before -- same
+// generated source, same compiler -- loads the cubin from <directory>/<hash of the source>.cubin instead of compiling.
+static std::string cache_file(const std::string &source) {
+    const char *dir = std::getenv("FAMSEQ_JIT_CACHE_DIR");
+    if (!dir || !*dir) return std::string();
+    unsigned long long h = 1469598103934665603ull; // FNV-1a over the source and the compiler version
+    auto mix = [&h](const char *p, size_t n) {
+        for (size_t i = 0; i < n; i++) {
+            h ^= (unsigned char)p[i];
+            h *= 1099511628211ull;
+        }
+    };
+    mix(source.data(), source.size());
+    const char *ver = "nvrtc-" FS_STR(CUDART_VERSION) "-sm_100a";
+    mix(ver, std::strlen(ver));
+    char name[64];
+    std::snprintf(name, sizeof name, "/%016llx.cubin", h);
+    return std::string(dir) + name;
+}
+
 int gibbs_jit_compile(const std::string &source, std::string &cubin, std::string &log, std::string &err) {
+    const std::string cached = cache_file(source);
+    if (!cached.empty()) {
+        if (FILE *f = std::fopen(cached.c_str(), "rb")) {
+            std::fseek(f, 0, SEEK_END);
+            const long n = std::ftell(f);
+            std::fseek(f, 0, SEEK_SET);
+            cubin.resize(n > 0 ? (size_t)n : 0);
+            const size_t got = cubin.empty() ? 0 : std::fread(&cubin[0], 1, cubin.size(), f);
+            std::fclose(f);
+            if (got == cubin.size() && got > 0) {
+                log = "cubin loaded from " + cached;
+                return FS_OK;
+            }
+            cubin.clear();
+        }
+    }
     const Nvrtc &N = nvrtc();
     if (!N.handle) {
         err = "run-time compilation unavailable: " + N.why;
@@ -596,6 +636,14 @@ int gibbs_jit_compile(const std::string &source, std::string &cubin, std::string
     if (rc != NVRTC_SUCCESS || cs == 0) {
         err = std::string("nvrtcGetCUBIN: ") + N.error_string(rc);
         return FS_E_CUDA;
+    }
+    if (!cached.empty()) { // best effort, atomic: write beside and rename
+        const std::string tmp = cached + ".tmp" + std::to_string((long long)getpid());
+        if (FILE *f = std::fopen(tmp.c_str(), "wb")) {
+            const bool ok = std::fwrite(cubin.data(), 1, cubin.size(), f) == cubin.size();
+            std::fclose(f);
+            if (!ok || std::rename(tmp.c_str(), cached.c_str()) != 0) std::remove(tmp.c_str());
+        }
     }
     return FS_OK;
 }

@@ -162,3 +162,21 @@ def test_generated_es_kernel_compiles_for_sm_100a(name):
     with fs.Engine(big.ids, big.mids, big.fids, big.genders, big.sequenced_cols(), device=-1) as e:
         with pytest.raises(fs.FamSeqError):
             e.es_kernel()
+
+
+def test_generated_kernels_can_be_cached_on_disk(tmp_path, monkeypatch):
+    """FAMSEQ_JIT_CACHE_DIR: the second engine on the same pedigree loads the cubin instead of compiling."""
+    import time
+    monkeypatch.setenv("FAMSEQ_JIT_CACHE_DIR", str(tmp_path))
+    ped = synth.half_sibs()
+    sizes, times, logs = [], [], []
+    for _ in range(2):
+        with fs.Engine(ped.ids, ped.mids, ped.fids, ped.genders, ped.sequenced_cols(), device=-1) as e:
+            t0 = time.time()
+            log, n = e.gibbs_kernel(compile=True)
+            times.append(time.time() - t0)
+            sizes.append(n)
+            logs.append(log)
+    assert sizes[0] == sizes[1] > 0 and "cubin loaded from" in logs[1] and "cubin loaded from" not in logs[0]
+    assert len([f for f in os.listdir(tmp_path) if f.endswith(".cubin")]) == 1
+    assert times[1] < times[0]
