@@ -150,6 +150,63 @@ def ped100() -> PedFile:
     return _mk(rows[:100])
 
 
+def random_pedigree(seed: int, n_target: int, loops: bool = False, shuffle: bool = False, unsequenced: float = 0.0) -> PedFile:
+    """A random pedigree for compiler tests: marriages with fresh founders (several spouses per member allowed), 1-3
+    children per couple; with `loops`, marriages between existing members too (marriage / consanguinity loops).
+    Without `loops` the marriage graph is a forest by construction, i.e. Elston-Stewart applies.  `shuffle` permutes
+    the ped rows (children may precede their parents, as the reference allows), `unsequenced` is the fraction of
+    members without a sample column."""
+    rng = np.random.default_rng(seed)
+    rows = [(1, 0, 0, 1), (2, 0, 0, 2)]  # id, mother, father, sex (1 male, 2 female)
+    couples = [(2, 1)]
+    sex = {1: 1, 2: 2}
+    married = {(2, 1)}
+    nxt = 3
+    while len(rows) < n_target:
+        act = rng.random()
+        if act < 0.55 or not couples:  # children for a couple
+            mother, father = couples[rng.integers(len(couples))]
+            for _ in range(int(rng.integers(1, 4))):
+                if len(rows) >= n_target:
+                    break
+                g = int(rng.integers(1, 3))
+                rows.append((nxt, mother, father, g))
+                sex[nxt] = g
+                nxt += 1
+        elif act < (0.75 if loops else 2.0):  # somebody marries a fresh founder
+            p = int(rows[rng.integers(len(rows))][0])
+            g = 3 - sex[p]
+            rows.append((nxt, 0, 0, g))
+            sex[nxt] = g
+            pair = (p, nxt) if sex[p] == 2 else (nxt, p)
+            couples.append(pair)
+            married.add(pair)
+            nxt += 1
+        else:  # two existing members marry (may close a loop)
+            a, b = (int(rows[i][0]) for i in rng.integers(len(rows), size=2))
+            if sex[a] == sex[b]:
+                continue
+            pair = (a, b) if sex[a] == 2 else (b, a)
+            if pair in married:
+                continue
+            parents = {r[0]: (r[1], r[2]) for r in rows}
+            if pair[0] in parents[pair[1]] or pair[1] in parents[pair[0]]:
+                continue  # no parent-child marriages
+            couples.append(pair)
+            married.add(pair)
+    # couples without children are dropped by construction of the ped file (a marriage only shows through children)
+    if shuffle:
+        rows = [rows[i] for i in rng.permutation(len(rows))]
+    ped = _mk(rows)
+    if unsequenced > 0:
+        for i in range(ped.n):
+            if rng.random() < unsequenced:
+                ped.names[i] = "NA"
+        if not ped.sequenced_cols():
+            ped.names[0] = "s00"
+    return ped
+
+
 PEDIGREES = {"trio": trio, "ped14": ped14, "ped40": ped40, "half_sibs": half_sibs, "three_wives": three_wives, "ped100": ped100,
              "cousins_loop": cousins_loop}
 
