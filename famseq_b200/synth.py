@@ -173,7 +173,7 @@ def random_pedigree(seed: int, n_target: int, loops: bool = False, shuffle: bool
                 rows.append((nxt, mother, father, g))
                 sex[nxt] = g
                 nxt += 1
-        elif act < (0.75 if loops else 2.0):  # somebody marries a fresh founder
+        elif act < (0.7 if loops else 2.0):  # somebody marries a fresh founder
             p = int(rows[rng.integers(len(rows))][0])
             g = 3 - sex[p]
             rows.append((nxt, 0, 0, g))
@@ -194,6 +194,13 @@ def random_pedigree(seed: int, n_target: int, loops: bool = False, shuffle: bool
                 continue  # no parent-child marriages
             couples.append(pair)
             married.add(pair)
+            for _ in range(int(rng.integers(1, 3))):  # the marriage shows (and can close a loop) only through children
+                if len(rows) >= n_target:
+                    break
+                g = int(rng.integers(1, 3))
+                rows.append((nxt, pair[0], pair[1], g))
+                sex[nxt] = g
+                nxt += 1
     # couples without children are dropped by construction of the ped file (a marriage only shows through children)
     if shuffle:
         rows = [rows[i] for i in rng.permutation(len(rows))]
