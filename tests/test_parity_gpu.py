@@ -416,3 +416,37 @@ def test_lrc_gate_shortcut_matches_division():
             got = e.run(fs.ES, lk, None)
         assert_parity(got, want, 0.0, f"lrc gate {lc}")
         assert np.array_equal(got.post, want["post"])
+
+
+# ------------------------------------------------------------------------------------------------------
+# random pedigrees (synth.random_pedigree): several spouses, childless married-in founders, shuffled ped rows,
+# unsequenced members, loops -- every method and every kernel against the oracle
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed", range(8))
+def test_random_pedigree_all_methods(seed, monkeypatch):
+    loops = seed % 4 == 3
+    ped = synth.random_pedigree(300 + seed, 5 + seed, loops=loops, shuffle=seed % 2 == 1, unsequenced=0.2 if seed % 3 == 0 else 0.0)
+    cols = ped.sequenced_cols()
+    S = len(cols)
+    lk, fl = synth.synth_likelihoods(synth._mk([(i, 0, 0, 1) for i in range(1, S + 1)]), 300, seed=500 + seed, x_fraction=0.3)
+    w_bn = O.run(ped, cols, lk[:24], fl[:24], method=O.BN)
+    w_mc = O.run(ped, cols, lk[:60], fl[:60], method=O.MCMC, burn=10, rep=80, rng=O.RNG_PHILOX, seed=9, v_offset=3)
+    results = {}
+    for jit in ("0", "1"):
+        monkeypatch.setenv("FAMSEQ_MCMC_JIT", jit)
+        monkeypatch.setenv("FAMSEQ_ES_JIT", jit)
+        with engine_for(ped, cols) as e:
+            has_loop = e.info()["has_loop"]
+            bn = e.run(fs.BN, lk[:24], fl[:24])
+            mc = e.run(fs.MCMC, lk[:60], fl[:60], burn=10, rep=80, seed=9, v_offset=3)
+            es = None if has_loop else e.run(fs.ES, lk, fl)
+        assert_parity(bn, w_bn, REL_TOL, f"random {seed} BN")
+        assert_parity(mc, w_mc, 1e-9, f"random {seed} MCMC jit={jit}")
+        if es is not None:
+            w_es = O.run(ped, cols, lk, fl, method=O.ES)
+            ok = w_es["status"] == 0
+            assert np.array_equal(es.status, w_es["status"]) and np.array_equal(es.post[ok], w_es["post"][ok]), f"random {seed} ES jit={jit}"
+        results[jit] = (mc, es)
+    assert np.array_equal(results["0"][0].post, results["1"][0].post, equal_nan=True)
+    if results["0"][1] is not None:
+        assert np.array_equal(results["0"][1].post, results["1"][1].post, equal_nan=True)
