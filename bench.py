@@ -389,7 +389,7 @@ def main():
         "dtype": "f64", "data": "synthetic", "config": config,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_variant": algorithmic_bytes(3),
-                     "kernel": "es_nuclear_kernel<1,128> (TMA bulk load/store, register-resident peeling)"},
+                     "kernel": "es_nuclear_kernel<1,32> (one warp per block, TMA bulk load/store of a 32-variant tile, register-resident peeling)"},
         "e2e": {"value": world * args.variants / e2e_s, "unit": "variants/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s * 1e3, "api": "fs_run() on pinned host buffers", "matches_device_path": same},
         "gpu_launches": launches, "clocks": clocks, "failed_variants": failed,
