@@ -71,17 +71,29 @@ int to_int(sv s) { // atoi
     return std::atoi(buf);
 }
 
+// Reads until end of file with a growing buffer, so that pipes and process substitutions (`-vcfFile <(zcat x.vcf.gz)`,
+// which the reference's ifstream/getline accepts) work like regular files; the size of a regular file is only a hint.
 bool read_file(const std::string &path, std::string &data) {
     FILE *f = std::fopen(path.c_str(), "rb");
     if (!f) return false;
-    std::fseek(f, 0, SEEK_END);
-    const long sz = std::ftell(f);
-    std::fseek(f, 0, SEEK_SET);
-    data.resize(sz > 0 ? (size_t)sz : 0);
-    const size_t got = data.empty() ? 0 : std::fread(&data[0], 1, data.size(), f);
+    size_t hint = 0;
+    if (std::fseek(f, 0, SEEK_END) == 0) {
+        const long sz = std::ftell(f);
+        if (sz > 0) hint = (size_t)sz;
+        std::fseek(f, 0, SEEK_SET);
+    }
+    data.clear();
+    size_t got = 0;
+    for (;;) {
+        if (data.size() - got < (1u << 16)) data.resize(std::max<size_t>({hint + 1, data.size() * 2, (size_t)1 << 20}));
+        const size_t n = std::fread(&data[got], 1, data.size() - got, f);
+        got += n;
+        if (n == 0) break;
+    }
+    const bool ok = !std::ferror(f);
     std::fclose(f);
     data.resize(got);
-    return true;
+    return ok;
 }
 
 // getline()-style cursor over an in-memory file.  Mirrors `while(!fin.eof()) getline(fin, line)`: after the last
@@ -306,14 +318,15 @@ class AsyncWriter {
         q_.push_back(std::move(s));
         cv_data_.notify_one();
     }
-    void close() { // drains the queue; the caller closes the FILE
+    bool close() { // drains the queue; the caller closes the FILE.  False when a write failed (disk full, ...)
         {
             std::lock_guard<std::mutex> lk(m_);
-            if (done_) return;
+            if (done_) return !failed_;
             done_ = true;
         }
         cv_data_.notify_one();
         th_.join();
+        return !failed_;
     }
 
   private:
@@ -328,10 +341,11 @@ class AsyncWriter {
                 q_.pop_front();
             }
             cv_space_.notify_one();
-            std::fwrite(s.data(), 1, s.size(), f_);
+            if (!failed_ && std::fwrite(s.data(), 1, s.size(), f_) != s.size()) failed_ = true; // keep draining so the producer never blocks
         }
     }
     FILE *f_;
+    bool failed_ = false; // written by the writer thread, read after join()
     std::mutex m_;
     std::condition_variable cv_data_, cv_space_;
     std::deque<std::string> q_;
@@ -757,10 +771,13 @@ bool run_vcf(const VcfOptions &opt, const PedRows &ped) {
     if (!engine_ready()) ok = false; // an input without records still reports a pedigree the engine rejects
     {
         const double t0 = now();
-        writer.close();
+        const bool written = writer.close();
         g_stats.drain_s = now() - t0;
+        if ((std::fclose(fout) != 0 || !written) && ok) {
+            std::cout << "Cannot write " << opt.output << std::endl;
+            ok = false;
+        }
     }
-    std::fclose(fout);
     g_stats.total_s = now() - t_start;
     emit_stats();
     return ok;
@@ -946,10 +963,13 @@ bool run_lk(const LkOptions &opt, const PedRows &ped) {
     if (!engine_ready()) ok = false; // an input without records still reports a pedigree the engine rejects
     {
         const double t0 = now();
-        writer.close();
+        const bool written = writer.close();
         g_stats.drain_s = now() - t0;
+        if ((std::fclose(fout) != 0 || !written) && ok) {
+            std::cout << "Cannot write " << opt.output << std::endl;
+            ok = false;
+        }
     }
-    std::fclose(fout);
     g_stats.total_s = now() - t_start;
     emit_stats();
     return ok;

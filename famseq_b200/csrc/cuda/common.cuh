@@ -29,10 +29,16 @@ struct BatchPtrs {
     const double *lk;     // [V][S][3]
     const uint8_t *flags; // [V] or nullptr
     double *post;         // [V][S][3]
-    double *single;       // [V][S][3]
+    double *single;       // [V][S][3]; nullptr = not wanted (only the nuclear-family kernel sees that: the engine gives
+                          // every other kernel a scratch buffer)
     uint8_t *gt;          // [V][S]
     uint8_t *status;      // [V]
     int64_t V;
+    // Compact input (fs_run_pl): integer Phred-scaled likelihoods [V][S][3], decoded as lut[pl] = pow(10, -pl/10) with
+    // the 65 536-entry table the engine built on the host with libm (file.cpp:588-590).  The nuclear-family kernel
+    // gathers from the table itself; for every other kernel the engine first expands pl into an FP64 scratch `lk`.
+    const uint16_t *pl = nullptr;
+    const double *lut = nullptr;
 };
 
 // Prior pair of one variant: `a` for females and for everybody on autosomes, `m` for males.

@@ -3,6 +3,7 @@
 // (one process, or one host thread) per device with the variants sharded between them.
 #include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <memory>
 #include <cstdio>
 #include <cstring>
@@ -12,9 +13,6 @@
 #include <vector>
 
 #include "../../../include/famseq_b200.h"
-#include "../host/bn_planner.hpp"
-#include "../host/es_compiler.hpp"
-#include "../host/mcmc_planner.hpp"
 #include "../host/pedigree.hpp"
 #include "es_jit.hpp"
 #include "gibbs_jit.hpp"
@@ -45,10 +43,20 @@ constexpr int kPipelineDepth = 3;
 struct DeviceChunk {
     cudaStream_t stream = nullptr;
     cudaEvent_t k0 = nullptr, k1 = nullptr;
-    double *lk = nullptr, *post = nullptr, *single = nullptr;
+    double *lk = nullptr, *post = nullptr, *single = nullptr; // lk / single are allocated when first needed
+    uint16_t *pl = nullptr;
     uint8_t *flags = nullptr, *gt = nullptr, *status = nullptr;
     int64_t capacity = 0; // variants
     int64_t in_flight = 0;
+};
+
+// What one batch call reads and writes: FP64 likelihoods or compact PL input, `single` optional.
+struct BatchIo {
+    const double *lk = nullptr;
+    const uint16_t *pl = nullptr;
+    const uint8_t *flags = nullptr;
+    double *post = nullptr, *single = nullptr;
+    uint8_t *gt = nullptr, *status = nullptr;
 };
 
 // Pedigree-specialised Gibbs kernel (gibbs_jit.cu).  FAMSEQ_MCMC_JIT: 0 = never, 1 = compile at the first MCMC batch and
@@ -116,9 +124,17 @@ struct fs_engine {
     GibbsJitState jit;
     EsJitState es_jit;
 
+    McmcTuning mcmc_tune;
+
+    std::vector<double> pl_table;          // lut[pl] = pow(10, -pl/10), host libm (file.cpp:588-590)
+    double *d_pl_table = nullptr;          // the same on the device, uploaded at the first fs_run_pl
+    unsigned long long *d_fixups = nullptr; // chains redone by the table-driven kernel after the generated one
+
     DeviceChunk chunk[kPipelineDepth];
     int64_t launches = 0, jit_launches = 0;
     double last_kernel_ms = 0;
+
+    std::vector<fs_engine *> parts; // fs_create_multi: one single-device engine per GPU (this one then has device -1)
 };
 
 extern "C" {
@@ -155,6 +171,7 @@ int fs_warmup(int device) {
 static void release_chunks(fs_engine *e) {
     for (DeviceChunk &c : e->chunk) {
         cudaFree(c.lk);
+        cudaFree(c.pl);
         cudaFree(c.post);
         cudaFree(c.single);
         cudaFree(c.flags);
@@ -169,6 +186,7 @@ static void release_chunks(fs_engine *e) {
 
 void fs_destroy(fs_engine *e) {
     if (!e) return;
+    for (fs_engine *part : e->parts) fs_destroy(part);
     if (e->jit.worker.joinable()) { // do not wait for a compile nobody will use
         if (e->jit.job && e->jit.job->state.load(std::memory_order_acquire) == GibbsJitJob::COMPILING)
             e->jit.worker.detach();
@@ -186,6 +204,8 @@ void fs_destroy(fs_engine *e) {
         gibbs_jit_unload(e->jit.kernel);
         es_jit_unload(e->es_jit.kernel);
         release_chunks(e);
+        cudaFree(e->d_pl_table);
+        cudaFree(e->d_fixups);
     }
     delete e;
 }
@@ -272,8 +292,8 @@ int fs_create(const fs_pedigree *ped, const fs_params *params, int device, fs_en
                     np.n_children++;
                 }
             e->is_nuclear = true;
-            const char *probe = std::getenv("FAMSEQ_ES_IO_PROBE");
-            np.io_probe = probe && probe[0] == '1';
+            np.tb = 32;
+            if (const char *env = std::getenv("FAMSEQ_ES_TB")) np.tb = std::atoi(env) == 64 ? 64 : 32;
         }
         const char *env = std::getenv("FAMSEQ_ES_GENERIC");
         e->force_generic_es = env && env[0] == '1';
@@ -285,6 +305,11 @@ int fs_create(const fs_pedigree *ped, const fs_params *params, int device, fs_en
     if (const char *env = std::getenv("FAMSEQ_MCMC_JIT")) e->jit.mode = env[0] == '0' ? 0 : (env[0] == '1' ? 1 : 2);
     if (const char *env = std::getenv("FAMSEQ_JIT_MIN_WORK")) e->jit.min_work = std::atof(env);
     if (const char *env = std::getenv("FAMSEQ_ES_JIT")) e->es_jit.mode = env[0] == '0' ? 0 : (env[0] == '1' ? 1 : 2);
+    if (const char *env = std::getenv("FAMSEQ_MCMC_BLOCKS")) e->mcmc_tune.blocks_cap = std::max(1, std::atoi(env));
+    if (const char *env = std::getenv("FAMSEQ_MCMC_WGLOBAL")) e->mcmc_tune.wglobal = env[0] == '1';
+    // PL decode table: exactly the expression of the reference's VCF driver (file.cpp:588-590), evaluated by the host's libm
+    e->pl_table.resize(FS_PL_TABLE_SIZE);
+    for (int k = 0; k < FS_PL_TABLE_SIZE; k++) e->pl_table[k] = std::pow(10.0, -std::fabs((double)k) / 10.0);
 
     if (device >= 0) {
         cudaError_t crc = cudaSetDevice(device);
@@ -325,6 +350,31 @@ int fs_create(const fs_pedigree *ped, const fs_params *params, int device, fs_en
     return FS_OK;
 }
 
+int fs_create_multi(const fs_pedigree *ped, const fs_params *params, const int *devices, int ndev, fs_engine **out) {
+    if (!ped || !out || !devices || ndev < 1) return fail(FS_E_ARG, "fs_create_multi: null argument or no device");
+    *out = nullptr;
+    for (int a = 0; a < ndev; a++)
+        for (int b = 0; b < a; b++)
+            if (devices[a] == devices[b]) return fail(FS_E_ARG, "fs_create_multi: device listed twice");
+    if (ndev == 1) return fs_create(ped, params, devices[0], out);
+    // the front engine holds the host side (pedigree, tables, info); the parts own the GPUs
+    fs_engine *front = nullptr;
+    int rc = fs_create(ped, params, -1, &front);
+    if (rc != FS_OK) return rc;
+    for (int g = 0; g < ndev; g++) {
+        fs_engine *part = nullptr;
+        rc = devices[g] < 0 ? fail(FS_E_ARG, "fs_create_multi: negative device") : fs_create(ped, params, devices[g], &part);
+        if (rc != FS_OK) {
+            const std::string keep = g_last_error;
+            fs_destroy(front);
+            return fail(rc, keep);
+        }
+        front->parts.push_back(part);
+    }
+    *out = front;
+    return FS_OK;
+}
+
 int fs_get_info(const fs_engine *e, fs_info *out) {
     if (!e || !out) return fail(FS_E_ARG, "fs_get_info: null argument");
     std::memset(out, 0, sizeof *out);
@@ -337,9 +387,24 @@ int fs_get_info(const fs_engine *e, fs_info *out) {
     out->bn_levels = e->bn_rc == FS_OK ? e->bn.plan.n_levels : 0;
     out->bn_group = e->bn_rc == FS_OK ? e->bn.plan.group : 0;
     out->mcmc_links = e->mcmc_rc == FS_OK ? e->mcmc.plan.n_links : 0;
-    out->device = e->device;
+    out->device = e->parts.empty() ? e->device : e->parts[0]->device;
     out->kernel_launches = e->launches;
     out->jit_launches = e->jit_launches;
+    out->n_devices = e->parts.empty() ? (e->device >= 0 ? 1 : 0) : (int32_t)e->parts.size();
+    for (const fs_engine *part : e->parts) {
+        fs_info pi;
+        const int rc = fs_get_info(part, &pi);
+        if (rc != FS_OK) return rc;
+        out->kernel_launches += pi.kernel_launches;
+        out->jit_launches += pi.jit_launches;
+        out->mcmc_fixups += pi.mcmc_fixups;
+    }
+    if (e->device >= 0 && e->d_fixups) {
+        unsigned long long n = 0;
+        FS_CUDA(cudaSetDevice(e->device));
+        FS_CUDA(cudaMemcpy(&n, e->d_fixups, sizeof n, cudaMemcpyDeviceToHost));
+        out->mcmc_fixups += (int64_t)n;
+    }
     return FS_OK;
 }
 
@@ -412,9 +477,15 @@ int fs_get_es_kernel(const fs_engine *e, int compile, char *text, size_t capacit
     return FS_OK;
 }
 
+int fs_get_pl_table(const fs_engine *e, double *out) {
+    if (!e || !out) return fail(FS_E_ARG, "fs_get_pl_table: null argument");
+    std::memcpy(out, e->pl_table.data(), sizeof(double) * FS_PL_TABLE_SIZE);
+    return FS_OK;
+}
+
 void *fs_alloc_pinned(size_t bytes) {
     void *p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
         cudaGetLastError();
         return nullptr;
     }
@@ -498,160 +569,332 @@ static int es_jit_poll(fs_engine *e, double variants, EsJitKernel **out) {
     return FS_OK;
 }
 
-// One kernel launch for `B.V` variants already on the device.
-static int dispatch(fs_engine *e, int method, const BatchPtrs &B, int32_t burn, int32_t rep, uint64_t seed,
-                    int64_t v_offset, cudaStream_t stream) {
+// The decode table on the device (uploaded once, at the first compact-input batch of this engine).
+static int ensure_pl_table(fs_engine *e, cudaStream_t stream) {
+    if (e->d_pl_table) return FS_OK;
+    FS_CUDA(cudaMalloc(&e->d_pl_table, sizeof(double) * FS_PL_TABLE_SIZE));
+    FS_CUDA(cudaMemcpyAsync(e->d_pl_table, e->pl_table.data(), sizeof(double) * FS_PL_TABLE_SIZE, cudaMemcpyHostToDevice, stream));
+    FS_CUDA(cudaStreamSynchronize(stream)); // pl_table is pageable: do not leave a staged copy behind
+    return FS_OK;
+}
+
+// Kernel launch(es) for `B.V` variants already on the device.  B.pl (compact input) and B.single == nullptr are
+// handled by the nuclear-family kernel itself; every other kernel gets FP64 likelihoods (expanded into `lk_scratch`)
+// and a place to put the individual-only posteriors (`single_scratch`); both scratch buffers are stream-ordered
+// allocations when the caller (fs_run*_device) has none.
+static int dispatch(fs_engine *e, int method, BatchPtrs B, int32_t burn, int32_t rep, uint64_t seed, int64_t v_offset,
+                    cudaStream_t stream, double *lk_scratch = nullptr, double *single_scratch = nullptr) {
     if (B.V == 0) return FS_OK;
-    switch (method) {
-    case FS_METHOD_ES: {
-        if (e->es_rc != FS_OK) return fail(e->es_rc, e->es_err);
-        const bool tma_ok = ((reinterpret_cast<uintptr_t>(B.gt) | reinterpret_cast<uintptr_t>(B.status)) & 15u) == 0;
-        if (e->is_nuclear && tma_ok && !e->force_generic_es) {
-            FS_CUDA(launch_es_nuclear(e->nuclear, B, stream));
-            break;
-        }
-        EsJitKernel *jk = nullptr;
-        if (tma_ok && !e->force_generic_es) {
-            const int rc = es_jit_poll(e, (double)B.V, &jk);
-            if (rc != FS_OK) return rc;
-        }
-        if (jk) {
-            FS_CUDA(es_jit_launch(jk, B, stream));
-            e->jit_launches++;
-        } else {
-            FS_CUDA(launch_es(e->es, B, e->es_tb, stream));
-        }
-        break;
-    }
-    case FS_METHOD_BN: {
-        if (e->bn_rc != FS_OK) return fail(e->bn_rc, e->bn_err);
-        FS_CUDA(launch_bn(e->bn, B, e->sm_count, stream));
-        break;
-    }
-    case FS_METHOD_MCMC: {
+    if (method != FS_METHOD_ES && method != FS_METHOD_BN && method != FS_METHOD_MCMC)
+        return fail(FS_E_ARG, "method must be 1 (BN), 2 (ES) or 3 (MCMC)");
+    if (method == FS_METHOD_ES && e->es_rc != FS_OK) return fail(e->es_rc, e->es_err);
+    if (method == FS_METHOD_BN && e->bn_rc != FS_OK) return fail(e->bn_rc, e->bn_err);
+    if (method == FS_METHOD_MCMC) {
         if (e->mcmc_rc != FS_OK) return fail(e->mcmc_rc, e->mcmc_err);
         if (burn < 0 || rep <= 0) return fail(FS_E_ARG, "MCMC needs burn >= 0 and rep >= 1");
-        GibbsJitKernel *jk = nullptr;
-        const int rc = gibbs_jit_poll(e, (double)B.V * ((double)burn + rep) * e->ped.n, &jk);
+    }
+    if (B.pl) {
+        const int rc = ensure_pl_table(e, stream);
         if (rc != FS_OK) return rc;
+        B.lut = e->d_pl_table;
+    }
+    const bool tma_ok = ((reinterpret_cast<uintptr_t>(B.gt) | reinterpret_cast<uintptr_t>(B.status) | reinterpret_cast<uintptr_t>(B.pl)) & 15u) == 0;
+    if (method == FS_METHOD_ES && e->is_nuclear && tma_ok && !e->force_generic_es) {
+        FS_CUDA(launch_es_nuclear(e->nuclear, B, stream));
+        e->launches++;
+        return FS_OK;
+    }
+    // ---- every other kernel: FP64 likelihoods in, individual-only posteriors out ------------------------------
+    const size_t row_doubles = (size_t)B.V * (size_t)e->ped.s() * 3;
+    double *owned_lk = nullptr, *owned_single = nullptr;
+    auto release = [&]() {
+        if (owned_lk) cudaFreeAsync(owned_lk, stream);
+        if (owned_single) cudaFreeAsync(owned_single, stream);
+    };
+    if (B.pl) {
+        if (!lk_scratch) {
+            FS_CUDA(cudaMallocAsync(&owned_lk, std::max<size_t>(row_doubles, 2) * sizeof(double), stream));
+            lk_scratch = owned_lk;
+        }
+        const cudaError_t rc = launch_pl_decode(B.pl, B.lut, lk_scratch, (int64_t)row_doubles, stream);
+        if (rc != cudaSuccess) {
+            release();
+            return cuda_fail(rc, "launch_pl_decode");
+        }
+        e->launches++;
+        B.lk = lk_scratch;
+        B.pl = nullptr;
+    }
+    if (!B.single) {
+        if (!single_scratch) {
+            const cudaError_t rc = cudaMallocAsync(&owned_single, std::max<size_t>(row_doubles, 2) * sizeof(double), stream);
+            if (rc != cudaSuccess) {
+                release();
+                return cuda_fail(rc, "cudaMallocAsync(single scratch)");
+            }
+            single_scratch = owned_single;
+        }
+        B.single = single_scratch;
+    }
+    cudaError_t krc = cudaSuccess;
+    int frc = FS_OK;
+    switch (method) {
+    case FS_METHOD_ES: {
+        EsJitKernel *jk = nullptr;
+        if (tma_ok && !e->force_generic_es) frc = es_jit_poll(e, (double)B.V, &jk);
+        if (frc != FS_OK) break;
         if (jk) {
-            // the specialised kernel does autosomal chains whose weights stay in its fast range; it marks the others
-            // (chrX, denormal or huge weight sums) with status 2 for a second pass of the table-driven kernel
-            FS_CUDA(gibbs_jit_launch(jk, B, burn, rep, seed, v_offset, e->sm_count, stream));
-            FS_CUDA(launch_mcmc(e->mcmc, B, e->mcmc_tb, burn, rep, seed, v_offset, e->sm_count, stream, true));
+            krc = es_jit_launch(jk, B, stream);
+            e->jit_launches++;
+        } else {
+            krc = launch_es(e->es, B, e->es_tb, stream);
+        }
+        break;
+    }
+    case FS_METHOD_BN:
+        krc = launch_bn(e->bn, B, e->sm_count, stream);
+        break;
+    case FS_METHOD_MCMC: {
+        GibbsJitKernel *jk = nullptr;
+        frc = gibbs_jit_poll(e, (double)B.V * ((double)burn + rep) * e->ped.n, &jk);
+        if (frc != FS_OK) break;
+        if (jk) {
+            // the specialised kernel covers chains whose weight sums stay positive normal numbers away from the exponent
+            // limits; it marks the others with status 2 for a second pass of the table-driven kernel (counted in d_fixups)
+            if (!e->d_fixups) {
+                krc = cudaMalloc(&e->d_fixups, sizeof(unsigned long long));
+                if (krc == cudaSuccess) krc = cudaMemset(e->d_fixups, 0, sizeof(unsigned long long));
+                if (krc != cudaSuccess) break;
+            }
+            krc = gibbs_jit_launch(jk, B, burn, rep, seed, v_offset, e->sm_count, stream);
+            if (krc == cudaSuccess)
+                krc = launch_mcmc(e->mcmc, B, e->mcmc_tb, burn, rep, seed, v_offset, e->sm_count, stream, e->mcmc_tune, true, e->d_fixups);
             e->jit_launches++;
             e->launches++;
         } else
-            FS_CUDA(launch_mcmc(e->mcmc, B, e->mcmc_tb, burn, rep, seed, v_offset, e->sm_count, stream));
+            krc = launch_mcmc(e->mcmc, B, e->mcmc_tb, burn, rep, seed, v_offset, e->sm_count, stream, e->mcmc_tune);
         break;
     }
-    default:
-        return fail(FS_E_ARG, "method must be 1 (BN), 2 (ES) or 3 (MCMC)");
     }
+    release();
+    if (frc != FS_OK) return frc;
+    if (krc != cudaSuccess) return cuda_fail(krc, "kernel launch");
     e->launches++;
     return FS_OK;
+}
+
+static int run_device(fs_engine *e, int method, int64_t V, const BatchIo &io, int32_t burn, int32_t rep, uint64_t seed,
+                      int64_t v_offset, void *stream, const char *who) {
+    if (!e) return fail(FS_E_ARG, std::string(who) + ": null engine");
+    if (!e->parts.empty()) return fail(FS_E_ARG, std::string(who) + ": device buffers need a single-GPU engine (fs_create)");
+    if (e->device < 0) return fail(FS_E_CUDA, "engine was created without a device (there is no CPU fallback)");
+    if (V < 0 || (V > 0 && ((!io.lk && !io.pl) || !io.post || !io.gt || !io.status))) return fail(FS_E_ARG, std::string(who) + ": null buffer");
+    if ((reinterpret_cast<uintptr_t>(io.lk) | reinterpret_cast<uintptr_t>(io.post) | reinterpret_cast<uintptr_t>(io.single)) & 15u)
+        return fail(FS_E_ARG, std::string(who) + ": lk/post/single must be 16-byte aligned");
+    FS_CUDA(cudaSetDevice(e->device));
+    BatchPtrs B{io.lk, io.flags, io.post, io.single, io.gt, io.status, V};
+    B.pl = io.pl;
+    return dispatch(e, method, B, burn, rep, seed, v_offset, static_cast<cudaStream_t>(stream));
 }
 
 int fs_run_device(fs_engine *e, int method, int64_t V, const double *d_lk, const uint8_t *d_flags, int32_t burn,
                   int32_t rep, uint64_t seed, int64_t v_offset, double *d_post, double *d_single,
                   uint8_t *d_gt, uint8_t *d_status, void *stream) {
-    if (!e) return fail(FS_E_ARG, "fs_run_device: null engine");
-    if (e->device < 0) return fail(FS_E_CUDA, "engine was created without a device (there is no CPU fallback)");
-    if (V < 0 || (V > 0 && (!d_lk || !d_post || !d_single || !d_gt || !d_status)))
-        return fail(FS_E_ARG, "fs_run_device: null buffer");
-    if ((reinterpret_cast<uintptr_t>(d_lk) | reinterpret_cast<uintptr_t>(d_post) |
-         reinterpret_cast<uintptr_t>(d_single)) & 15u)
-        return fail(FS_E_ARG, "fs_run_device: lk/post/single must be 16-byte aligned");
-    FS_CUDA(cudaSetDevice(e->device));
-    BatchPtrs B{d_lk, d_flags, d_post, d_single, d_gt, d_status, V};
-    return dispatch(e, method, B, burn, rep, seed, v_offset, static_cast<cudaStream_t>(stream));
+    BatchIo io;
+    io.lk = d_lk, io.flags = d_flags, io.post = d_post, io.single = d_single, io.gt = d_gt, io.status = d_status;
+    return run_device(e, method, V, io, burn, rep, seed, v_offset, stream, "fs_run_device");
 }
 
-static int ensure_chunks(fs_engine *e, int64_t cap) {
+int fs_run_pl_device(fs_engine *e, int method, int64_t V, const uint16_t *d_pl, const uint8_t *d_flags, int32_t burn,
+                     int32_t rep, uint64_t seed, int64_t v_offset, double *d_post, double *d_single, uint8_t *d_gt,
+                     uint8_t *d_status, void *stream) {
+    BatchIo io;
+    io.pl = d_pl, io.flags = d_flags, io.post = d_post, io.single = d_single, io.gt = d_gt, io.status = d_status;
+    return run_device(e, method, V, io, burn, rep, seed, v_offset, stream, "fs_run_pl_device");
+}
+
+// Device buffers of the host pipeline: `cap` variants per slot; lk (FP64 input, or the expansion of compact input for the
+// kernels that need it), pl and single only when this call uses them.
+static int ensure_chunks(fs_engine *e, int64_t cap, bool need_lk, bool need_pl, bool need_single) {
     const size_t S = (size_t)e->ped.s();
     for (DeviceChunk &c : e->chunk) {
-        if (c.capacity >= cap) continue;
-        cudaStream_t st = c.stream;
-        cudaEvent_t k0 = c.k0, k1 = c.k1;
-        cudaFree(c.lk);
-        cudaFree(c.post);
-        cudaFree(c.single);
-        cudaFree(c.flags);
-        cudaFree(c.gt);
-        cudaFree(c.status);
-        c = DeviceChunk();
-        c.stream = st;
-        c.k0 = k0;
-        c.k1 = k1;
-        if (!c.stream) FS_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-        if (!c.k0) FS_CUDA(cudaEventCreate(&c.k0));
-        if (!c.k1) FS_CUDA(cudaEventCreate(&c.k1));
-        const size_t nd = (size_t)cap * S * 3 * sizeof(double);
-        FS_CUDA(cudaMalloc(&c.lk, nd ? nd : 16));
-        FS_CUDA(cudaMalloc(&c.post, nd ? nd : 16));
-        FS_CUDA(cudaMalloc(&c.single, nd ? nd : 16));
-        FS_CUDA(cudaMalloc(&c.flags, (size_t)cap));
-        FS_CUDA(cudaMalloc(&c.gt, S ? (size_t)cap * S : 16));
-        FS_CUDA(cudaMalloc(&c.status, (size_t)cap));
-        c.capacity = cap;
+        if (c.capacity < cap) {
+            cudaStream_t st = c.stream;
+            cudaEvent_t k0 = c.k0, k1 = c.k1;
+            cudaFree(c.lk);
+            cudaFree(c.pl);
+            cudaFree(c.post);
+            cudaFree(c.single);
+            cudaFree(c.flags);
+            cudaFree(c.gt);
+            cudaFree(c.status);
+            c = DeviceChunk();
+            c.stream = st;
+            c.k0 = k0;
+            c.k1 = k1;
+            if (!c.stream) FS_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+            if (!c.k0) FS_CUDA(cudaEventCreate(&c.k0));
+            if (!c.k1) FS_CUDA(cudaEventCreate(&c.k1));
+            const size_t nd = (size_t)cap * S * 3 * sizeof(double);
+            FS_CUDA(cudaMalloc(&c.post, nd ? nd : 16));
+            FS_CUDA(cudaMalloc(&c.flags, (size_t)cap));
+            FS_CUDA(cudaMalloc(&c.gt, S ? (size_t)cap * S : 16));
+            FS_CUDA(cudaMalloc(&c.status, (size_t)cap));
+            c.capacity = cap;
+        }
+        const size_t nd = std::max<size_t>((size_t)c.capacity * S * 3 * sizeof(double), 16);
+        if (need_lk && !c.lk) FS_CUDA(cudaMalloc(&c.lk, nd));
+        if (need_single && !c.single) FS_CUDA(cudaMalloc(&c.single, nd));
+        if (need_pl && !c.pl) FS_CUDA(cudaMalloc(&c.pl, std::max<size_t>((size_t)c.capacity * S * 3 * sizeof(uint16_t), 16)));
     }
     return FS_OK;
 }
 
-int fs_run(fs_engine *e, int method, int64_t V, const double *lk, const uint8_t *flags, int32_t burn, int32_t rep,
-           uint64_t seed, int64_t v_offset, double *post, double *single, uint8_t *gt, uint8_t *status) {
-    if (!e) return fail(FS_E_ARG, "fs_run: null engine");
+// The pipelined batch call of ONE GPU on host buffers.
+static int run_host_one(fs_engine *e, int method, int64_t V, const BatchIo &io, int32_t burn, int32_t rep, uint64_t seed,
+                        int64_t v_offset) {
     if (e->device < 0) return fail(FS_E_CUDA, "engine was created without a device (there is no CPU fallback)");
-    if (V < 0 || (V > 0 && (!lk || !post || !single || !gt || !status))) return fail(FS_E_ARG, "fs_run: null buffer");
     if (V == 0) return FS_OK;
     FS_CUDA(cudaSetDevice(e->device));
     const size_t S = (size_t)e->ped.s();
-    // Chunks of ~48 MB of likelihoods (a multiple of 1024 variants keeps every tile 16-byte aligned)
+    // Chunks of ~48 MB of FP64 likelihoods (a multiple of 1024 variants keeps every tile 16-byte aligned)
     // are cycled through kPipelineDepth streams so that the H2D copy of chunk k+1, the kernel of
     // chunk k and the D2H copy of chunk k-1 overlap.
     int64_t cap = (int64_t)((48u << 20) / (S ? S * 24 : 24));
     cap = std::max<int64_t>(1024, std::min<int64_t>(cap, 1 << 22)) & ~(int64_t)1023;
     cap = std::min<int64_t>(cap, (V + 1023) & ~(int64_t)1023);
-    int rc = ensure_chunks(e, cap);
+    const bool fused = method == FS_METHOD_ES && e->is_nuclear && !e->force_generic_es; // kernel reads pl / skips single itself
+    int rc = ensure_chunks(e, cap, !io.pl || !fused, io.pl != nullptr, io.single != nullptr || !fused);
     if (rc != FS_OK) return rc;
 
     e->last_kernel_ms = 0;
     auto drain = [&](DeviceChunk &c) -> int {
         if (!c.in_flight) return FS_OK;
+        c.in_flight = 0;
         FS_CUDA(cudaStreamSynchronize(c.stream));
         float ms = 0;
         FS_CUDA(cudaEventElapsedTime(&ms, c.k0, c.k1));
         e->last_kernel_ms += ms;
-        c.in_flight = 0;
+        return FS_OK;
+    };
+    auto submit = [&](DeviceChunk &c, int64_t v0) -> int {
+        const int64_t nv = std::min<int64_t>(cap, V - v0);
+        const size_t nd = (size_t)nv * S * 3 * sizeof(double);
+        c.in_flight = nv; // from here on the slot has work queued that touches the caller's buffers
+        if (nd && io.pl)
+            FS_CUDA(cudaMemcpyAsync(c.pl, io.pl + (size_t)v0 * S * 3, nd / 4, cudaMemcpyHostToDevice, c.stream));
+        else if (nd)
+            FS_CUDA(cudaMemcpyAsync(c.lk, io.lk + (size_t)v0 * S * 3, nd, cudaMemcpyHostToDevice, c.stream));
+        if (io.flags) FS_CUDA(cudaMemcpyAsync(c.flags, io.flags + v0, (size_t)nv, cudaMemcpyHostToDevice, c.stream));
+        BatchPtrs B{io.pl ? nullptr : c.lk, io.flags ? c.flags : nullptr, c.post, io.single ? c.single : nullptr, c.gt, c.status, nv};
+        B.pl = io.pl ? c.pl : nullptr;
+        FS_CUDA(cudaEventRecord(c.k0, c.stream));
+        const int drc = dispatch(e, method, B, burn, rep, seed, v_offset + v0, c.stream, c.lk, c.single);
+        if (drc != FS_OK) return drc;
+        FS_CUDA(cudaEventRecord(c.k1, c.stream));
+        if (nd) {
+            FS_CUDA(cudaMemcpyAsync(io.post + (size_t)v0 * S * 3, c.post, nd, cudaMemcpyDeviceToHost, c.stream));
+            if (io.single) FS_CUDA(cudaMemcpyAsync(io.single + (size_t)v0 * S * 3, c.single, nd, cudaMemcpyDeviceToHost, c.stream));
+            FS_CUDA(cudaMemcpyAsync(io.gt + (size_t)v0 * S, c.gt, (size_t)nv * S, cudaMemcpyDeviceToHost, c.stream));
+        }
+        FS_CUDA(cudaMemcpyAsync(io.status + v0, c.status, (size_t)nv, cudaMemcpyDeviceToHost, c.stream));
         return FS_OK;
     };
     int slot = 0;
-    for (int64_t v0 = 0; v0 < V; v0 += cap, slot = (slot + 1) % kPipelineDepth) {
+    for (int64_t v0 = 0; v0 < V && rc == FS_OK; v0 += cap, slot = (slot + 1) % kPipelineDepth) {
         DeviceChunk &c = e->chunk[slot];
-        if ((rc = drain(c)) != FS_OK) return rc;
-        const int64_t nv = std::min<int64_t>(cap, V - v0);
-        const size_t nd = (size_t)nv * S * 3 * sizeof(double);
-        if (nd) FS_CUDA(cudaMemcpyAsync(c.lk, lk + (size_t)v0 * S * 3, nd, cudaMemcpyHostToDevice, c.stream));
-        if (flags) FS_CUDA(cudaMemcpyAsync(c.flags, flags + v0, (size_t)nv, cudaMemcpyHostToDevice, c.stream));
-        BatchPtrs B{c.lk, flags ? c.flags : nullptr, c.post, c.single, c.gt, c.status, nv};
-        FS_CUDA(cudaEventRecord(c.k0, c.stream));
-        rc = dispatch(e, method, B, burn, rep, seed, v_offset + v0, c.stream);
-        if (rc != FS_OK) return rc;
-        FS_CUDA(cudaEventRecord(c.k1, c.stream));
-        if (nd) {
-            FS_CUDA(cudaMemcpyAsync(post + (size_t)v0 * S * 3, c.post, nd, cudaMemcpyDeviceToHost, c.stream));
-            FS_CUDA(cudaMemcpyAsync(single + (size_t)v0 * S * 3, c.single, nd, cudaMemcpyDeviceToHost, c.stream));
-            FS_CUDA(cudaMemcpyAsync(gt + (size_t)v0 * S, c.gt, (size_t)nv * S, cudaMemcpyDeviceToHost, c.stream));
-        }
-        FS_CUDA(cudaMemcpyAsync(status + v0, c.status, (size_t)nv, cudaMemcpyDeviceToHost, c.stream));
-        c.in_flight = nv;
+        if ((rc = drain(c)) != FS_OK) break;
+        rc = submit(c, v0);
     }
-    for (DeviceChunk &c : e->chunk)
-        if ((rc = drain(c)) != FS_OK) return rc;
+    if (rc != FS_OK) {
+        // Something failed half way: copies into the caller's buffers may still be queued on the other slots.  Wait for
+        // all of them (ignoring secondary errors) so that the caller may release its buffers, then report the first error.
+        const std::string first = g_last_error;
+        for (DeviceChunk &c : e->chunk)
+            if (c.in_flight) {
+                cudaStreamSynchronize(c.stream);
+                c.in_flight = 0;
+            }
+        cudaGetLastError();
+        return fail(rc, first);
+    }
+    for (DeviceChunk &c : e->chunk) {
+        const int drc = drain(c);
+        if (drc != FS_OK && rc == FS_OK) rc = drc; // keep draining the other slots
+    }
+    return rc;
+}
+
+// Host-buffer entry: argument checks, then one GPU, or (fs_create_multi) one contiguous slice per GPU on its own thread.
+static int run_host(fs_engine *e, int method, int64_t V, const BatchIo &io, int32_t burn, int32_t rep, uint64_t seed,
+                    int64_t v_offset, const char *who) {
+    if (!e) return fail(FS_E_ARG, std::string(who) + ": null engine");
+    if (V < 0 || (V > 0 && ((!io.lk && !io.pl) || !io.post || !io.gt || !io.status))) return fail(FS_E_ARG, std::string(who) + ": null buffer");
+    if (e->parts.empty()) return run_host_one(e, method, V, io, burn, rep, seed, v_offset);
+    const int G = (int)e->parts.size();
+    const size_t S = (size_t)e->ped.s();
+    std::vector<int> rcs(G, FS_OK);
+    std::vector<std::string> errs(G);
+    auto work = [&](int g) {
+        // slice boundaries on multiples of 1024 variants keep every GPU's tiles 16-byte aligned in the caller's buffers
+        auto cut = [&](int k) { return k >= G ? V : std::min<int64_t>(V, (((V / G) * k) + 1023) & ~(int64_t)1023); };
+        const int64_t a = cut(g), b = cut(g + 1);
+        if (b <= a) return;
+        BatchIo part = io;
+        if (io.lk) part.lk = io.lk + (size_t)a * S * 3;
+        if (io.pl) part.pl = io.pl + (size_t)a * S * 3;
+        if (io.flags) part.flags = io.flags + a;
+        part.post = io.post + (size_t)a * S * 3;
+        if (io.single) part.single = io.single + (size_t)a * S * 3;
+        part.gt = io.gt + (size_t)a * S;
+        part.status = io.status + a;
+        rcs[g] = run_host_one(e->parts[g], method, b - a, part, burn, rep, seed, v_offset + a);
+        if (rcs[g] != FS_OK) errs[g] = g_last_error; // thread-local: carry it to the caller's thread
+    };
+    std::vector<std::thread> threads;
+    for (int g = 1; g < G; g++) threads.emplace_back(work, g);
+    work(0);
+    for (std::thread &t : threads) t.join();
+    e->last_kernel_ms = 0;
+    for (int g = 0; g < G; g++) e->last_kernel_ms = std::max(e->last_kernel_ms, e->parts[g]->last_kernel_ms);
+    for (int g = 0; g < G; g++)
+        if (rcs[g] != FS_OK) return fail(rcs[g], "device " + std::to_string(e->parts[g]->device) + ": " + errs[g]);
     return FS_OK;
 }
 
+int fs_run(fs_engine *e, int method, int64_t V, const double *lk, const uint8_t *flags, int32_t burn, int32_t rep,
+           uint64_t seed, int64_t v_offset, double *post, double *single, uint8_t *gt, uint8_t *status) {
+    BatchIo io;
+    io.lk = lk, io.flags = flags, io.post = post, io.single = single, io.gt = gt, io.status = status;
+    return run_host(e, method, V, io, burn, rep, seed, v_offset, "fs_run");
+}
+
+int fs_run_pl(fs_engine *e, int method, int64_t V, const uint16_t *pl, const uint8_t *flags, int32_t burn, int32_t rep,
+              uint64_t seed, int64_t v_offset, double *post, double *single, uint8_t *gt, uint8_t *status) {
+    BatchIo io;
+    io.pl = pl, io.flags = flags, io.post = post, io.single = single, io.gt = gt, io.status = status;
+    return run_host(e, method, V, io, burn, rep, seed, v_offset, "fs_run_pl");
+}
+
 } // extern "C"
+
+// ---- compact input: lk[k] = lut[pl[k]] ----------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) pl_decode_kernel(const uint16_t *__restrict__ pl, const double *__restrict__ lut,
+                                                        double *__restrict__ lk, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) lk[k] = __ldg(lut + pl[k]);
+}
+} // namespace
+
+namespace famseq {
+cudaError_t launch_pl_decode(const uint16_t *pl, const double *lut, double *lk, int64_t n, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    const int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
+    pl_decode_kernel<<<grid, 256, 0, stream>>>(pl, lut, lk, n);
+    return cudaGetLastError();
+}
+} // namespace famseq
 
 // ---- FP64 roofline probe ----------------------------------------------------------------------------
 // Register-resident DFMA chains (8 independent accumulators per thread): the measured FP64 peak that

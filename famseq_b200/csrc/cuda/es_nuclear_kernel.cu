@@ -17,7 +17,7 @@
 //     global traffic is fully coalesced 16-byte-granular and costs no LSU wavefronts.
 // HBM-bound: 73*S+2 algorithmic bytes per variant (221 B for a trio).
 #include <algorithm>
-#include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 #include "kernels.hpp"
@@ -72,54 +72,69 @@ struct Row3 {
     double v[3];
 };
 
-__device__ __forceinline__ Row3 load_lk(const double *in_row, int col) {
+// Likelihood row of input column `col` of this thread's variant: FP64 as it stands, or (compact input, fs_run_pl)
+// integer Phred-scaled likelihoods decoded through the host-built table lut[pl] = pow(10, -pl/10) (file.cpp:588-590).
+template <bool PL> __device__ __forceinline__ Row3 load_lk(const void *in_row, const double *__restrict__ lut, int col) {
     Row3 r;
-    if (col >= 0) {
-        r.v[0] = in_row[col * 3];
-        r.v[1] = in_row[col * 3 + 1];
-        r.v[2] = in_row[col * 3 + 2];
-    } else {
+    if (col < 0) {
         r.v[0] = r.v[1] = r.v[2] = 1.0; // unsequenced member (file.cpp:565)
+    } else if (PL) {
+        const uint16_t *q = static_cast<const uint16_t *>(in_row) + col * 3;
+        r.v[0] = __ldg(lut + q[0]);
+        r.v[1] = __ldg(lut + q[1]);
+        r.v[2] = __ldg(lut + q[2]);
+    } else {
+        const double *q = static_cast<const double *>(in_row) + col * 3;
+        r.v[0] = q[0];
+        r.v[1] = q[1];
+        r.v[2] = q[2];
     }
     return r;
 }
 
+// Where a thread's results go: its rows of the post / gt tiles in shared memory.
+struct OutRows {
+    double *post;
+    uint8_t *gt;
+    __device__ __forceinline__ void put(int col, double p0, double p1, double p2) const {
+        if (col < 0) return; // unsequenced member: nothing is reported for it
+        post[col * 3] = p0;
+        post[col * 3 + 1] = p1;
+        post[col * 3 + 2] = p2;
+        gt[col] = call_genotype(p0, p1, p2);
+    }
+};
+
 // marginal of one member: v = (m * l) * a, row sum == 0 fails the variant (family.cpp:1296-1314)
-__device__ __forceinline__ bool finish(const Row3 &m, const Row3 &l, const Row3 &a, int col, double *post_row) {
-    const double v0 = (m.v[0] * l.v[0]) * a.v[0], v1 = (m.v[1] * l.v[1]) * a.v[1], v2 = (m.v[2] * l.v[2]) * a.v[2];
+__device__ __forceinline__ bool finish(const Row3 &ml, const Row3 &a, const OutRows &out, int col) {
+    const double v0 = ml.v[0] * a.v[0], v1 = ml.v[1] * a.v[1], v2 = ml.v[2] * a.v[2];
     const double sum = (v0 + v1) + v2;
-    if (col >= 0) div3(v0, v1, v2, sum, post_row[col * 3], post_row[col * 3 + 1], post_row[col * 3 + 2]);
+    double p0, p1, p2;
+    div3(v0, v1, v2, sum, p0, p1, p2);
+    out.put(col, p0, p1, p2);
     return sum == 0.0;
 }
 
-// The peeling of a nuclear family; returns true when the reference would return false.
+// The peeling of a nuclear family; returns true when the reference would return false.  Rows are indexed by ROLE:
+// 0 father, 1 mother, 2.. children in ped order.  wf / wm = prior * lk of the founders (the numerators of their
+// individual-only posteriors: the same products, formed once).
 template <int NC, bool X>
-__device__ __forceinline__ bool peel(const NuclearParams &P, const VariantPriors &pr, const double *in_row, double *post_row) {
+__device__ __forceinline__ bool peel(const NuclearParams &P, const VariantPriors &pr, const Row3 (&L)[NC + 2], const Row3 &wf, const Row3 &wm,
+                                     const int (&col)[NC + 2], const OutRows &out) {
     const RunConstants &C = P.C;
-    const Row3 lf = load_lk(in_row, P.col_father), lm = load_lk(in_row, P.col_mother);
-    Row3 wf, wm, prior_f, prior_m, one;
-#pragma unroll
-    for (int g = 0; g < 3; g++) {
-        prior_f.v[g] = pr.m[g]; // the father is male: chrX male prior on X (family.cpp:1281-1290 / :1337-1358)
-        prior_m.v[g] = pr.a[g];
-        wf.v[g] = prior_f.v[g] * lf.v[g]; // ant * lk
-        wm.v[g] = prior_m.v[g] * lm.v[g];
-        one.v[g] = 1.0;
-    }
     // K[c][a][b] = sum_l (T_c[l][a][b] * lk_c[l])
-    Row3 lc[NC];
     double K[NC][3][3];
 #pragma unroll
     for (int c = 0; c < NC; c++) {
-        lc[c] = load_lk(in_row, P.col_child[c]);
+        const Row3 &lc = L[2 + c];
         const int sel = P.male_child[c] ? K_TAB_XM : K_TAB_XF;
 #pragma unroll
         for (int a = 0; a < 3; a++)
 #pragma unroll
             for (int b = 0; b < 3; b++) {
-                double sc = trans<X>(C, sel, 0, a, b) * lc[c].v[0];
-                sc = sc + trans<X>(C, sel, 1, a, b) * lc[c].v[1];
-                sc = sc + trans<X>(C, sel, 2, a, b) * lc[c].v[2];
+                double sc = trans<X>(C, sel, 0, a, b) * lc.v[0];
+                sc = sc + trans<X>(C, sel, 1, a, b) * lc.v[1];
+                sc = sc + trans<X>(C, sel, 2, a, b) * lc.v[2];
                 K[c][a][b] = sc;
             }
     }
@@ -136,22 +151,28 @@ __device__ __forceinline__ bool peel(const NuclearParams &P, const VariantPriors
         }
     // posterior messages.  Autosome: the table index is (own genotype, spouse genotype) for both parents
     // (family.cpp:1836); chrX: (mother, father) (family.cpp:1900-1921).
-    Row3 pos_f, pos_m;
+    Row3 pl_f, pl_m; // (posterior message * lk) of the founders
 #pragma unroll
     for (int g = 0; g < 3; g++) {
         double a = wf.v[0] * kids[g][0]; // mother g, father b
         a = a + wf.v[1] * kids[g][1];
         a = a + wf.v[2] * kids[g][2];
-        pos_m.v[g] = a;
+        pl_m.v[g] = a * L[1].v[g];
         double f = wm.v[0] * (X ? kids[0][g] : kids[g][0]);
         f = f + wm.v[1] * (X ? kids[1][g] : kids[g][1]);
         f = f + wm.v[2] * (X ? kids[2][g] : kids[g][2]);
-        pos_f.v[g] = f;
+        pl_f.v[g] = f * L[0].v[g];
+    }
+    Row3 prior_f, prior_m;
+#pragma unroll
+    for (int g = 0; g < 3; g++) {
+        prior_f.v[g] = pr.m[g]; // the father is male: chrX male prior on X (family.cpp:1281-1290 / :1337-1358)
+        prior_m.v[g] = pr.a[g];
     }
     bool failed = false;
-    // FIN in ped order does not matter for the values; every member's row sum is checked.
-    failed |= finish(pos_f, lf, prior_f, P.col_father, post_row);
-    failed |= finish(pos_m, lm, prior_m, P.col_mother, post_row);
+    // every member's row sum is checked (the order of the members does not matter for the values)
+    failed |= finish(pl_f, prior_f, out, col[0]);
+    failed |= finish(pl_m, prior_m, out, col[1]);
 #pragma unroll
     for (int c = 0; c < NC; c++) {
         const int sel = P.male_child[c] ? K_TAB_XM : K_TAB_XF;
@@ -182,106 +203,139 @@ __device__ __forceinline__ bool peel(const NuclearParams &P, const VariantPriors
             }
             ant.v[g] = over_m;
         }
-        failed |= finish(one, lc[c], ant, P.col_child[c], post_row);
+        failed |= finish(L[2 + c], ant, out, col[2 + c]); // the posterior message of a childless member is (1, 1, 1): 1 * lk = lk
     }
     return failed;
 }
 
 // One variant: individual-only posterior, LRC gate, peeling, genotype calls -- from the thread's row of the input tile
-// into its rows of the output tiles (all in shared memory).
-template <int NC>
-__device__ __forceinline__ void variant_thread(const NuclearParams &P, const VariantPriors &pr, unsigned flag, int tid, const double *s_in,
-                                               double *s_post, double *s_single, uint8_t *s_gt, uint8_t *s_status) {
+// into its rows of the output tiles (all in shared memory).  Everything in between lives in registers, indexed by role.
+template <int NC, bool PL, bool SINGLE>
+__device__ __forceinline__ void variant_thread(const NuclearParams &P, unsigned flag, const void *in_row, const double *__restrict__ lut,
+                                               double *post_row, double *single_row, uint8_t *gt_row, uint8_t *status) {
+    constexpr int NR = NC + 2;
     const RunConstants &C = P.C;
-    const int S = C.s, S3 = 3 * S;
-    if (P.io_probe) { // I/O ceiling probe: same tiles in and out, no arithmetic
-        for (int k = 0; k < S3; k++) s_post[tid * S3 + k] = s_single[tid * S3 + k] = s_in[tid * S3 + k];
-        for (int c = 0; c < S; c++) s_gt[tid * S + c] = 0;
-        s_status[tid] = 0;
-    } else {
-        const double *in_row = s_in + tid * S3;
-        double *post_row = s_post + tid * S3;
-        double *single_row = s_single + tid * S3;
-        // individual-only posterior (family.cpp:1405-1499) and LRC gate (family.cpp:1140-1162)
-        bool failed = C.unseq_fail[flag & 3u] != 0;
-        bool pedigree_needed = false;
-        for (int c = 0; c < S; c++) {
-            const double l0 = in_row[c * 3], l1 = in_row[c * 3 + 1], l2 = in_row[c * 3 + 2];
-            const bool male = C.col_male[c] != 0;
-            const double r0 = l0 * (male ? pr.m[0] : pr.a[0]);
-            const double r1 = l1 * (male ? pr.m[1] : pr.a[1]);
-            const double r2 = l2 * (male ? pr.m[2] : pr.a[2]);
-            const double rs = (r0 + r1) + r2;
-            if (rs <= 0.0) failed = true;
-            div3(r0, r1, r2, rs, single_row[c * 3], single_row[c * 3 + 1], single_row[c * 3 + 2]);
-            double big = 0.0;
-            if (big < l0) big = l0;
-            if (big < l1) big = l1;
-            if (big < l2) big = l2;
-            const double ls = (l0 + l1) + l2;
-            if (lrc_wants_pedigree(C.lrc, l0, l1, l2, big, ls)) pedigree_needed = true;
-        }
-        if (!failed) {
-            if (!pedigree_needed) {
-                for (int k = 0; k < S3; k++) post_row[k] = single_row[k];
-            } else if ((flag >> 1) & 1u) {
-                failed = peel<NC, true>(P, pr, in_row, post_row);
-            } else {
-                failed = peel<NC, false>(P, pr, in_row, post_row);
-            }
-        }
-        if (failed)
-            for (int k = 0; k < S3; k++) post_row[k] = single_row[k] = 0.0;
-        for (int c = 0; c < S; c++)
-            s_gt[tid * S + c] = failed ? (uint8_t)255 : call_genotype(post_row[c * 3], post_row[c * 3 + 1], post_row[c * 3 + 2]);
-        s_status[tid] = failed ? 1 : 0;
+    const VariantPriors pr = select_priors(C, flag);
+    int col[NR];
+    bool male[NR];
+    col[0] = P.col_father;
+    col[1] = P.col_mother;
+    male[0] = true;
+    male[1] = false;
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        col[2 + c] = P.col_child[c];
+        male[2 + c] = P.male_child[c] != 0;
     }
+    // individual-only posterior (family.cpp:1405-1499) and LRC gate (family.cpp:1140-1162)
+    const OutRows out{post_row, gt_row};
+    Row3 L[NR], W[2]; // lk of every role; lk * prior of the founders (also their "anterior * lk" in the peeling)
+    bool failed = C.unseq_fail[flag & 3u] != 0;
+    bool pedigree_needed = false;
+#pragma unroll
+    for (int r = 0; r < NR; r++) {
+        L[r] = load_lk<PL>(in_row, lut, col[r]);
+        const double w0 = L[r].v[0] * (male[r] ? pr.m[0] : pr.a[0]);
+        const double w1 = L[r].v[1] * (male[r] ? pr.m[1] : pr.a[1]);
+        const double w2 = L[r].v[2] * (male[r] ? pr.m[2] : pr.a[2]);
+        if (r < 2) W[r].v[0] = w0, W[r].v[1] = w1, W[r].v[2] = w2;
+        if (col[r] >= 0) {
+            const double rs = (w0 + w1) + w2;
+            if (rs <= 0.0) failed = true;
+            if (SINGLE) {
+                const int k = col[r] * 3;
+                div3(w0, w1, w2, rs, single_row[k], single_row[k + 1], single_row[k + 2]);
+            }
+            double big = 0.0;
+            if (big < L[r].v[0]) big = L[r].v[0];
+            if (big < L[r].v[1]) big = L[r].v[1];
+            if (big < L[r].v[2]) big = L[r].v[2];
+            const double ls = (L[r].v[0] + L[r].v[1]) + L[r].v[2];
+            if (lrc_wants_pedigree(C.lrc, L[r].v[0], L[r].v[1], L[r].v[2], big, ls)) pedigree_needed = true;
+        }
+    }
+    if (!failed) {
+        if (!pedigree_needed) { // FPP := GPP (family.cpp:1164-1249); rare with the default -LRC 1
+#pragma unroll
+            for (int r = 0; r < NR; r++) {
+                if (col[r] < 0) continue;
+                double p0, p1, p2;
+                if (SINGLE) {
+                    p0 = single_row[col[r] * 3], p1 = single_row[col[r] * 3 + 1], p2 = single_row[col[r] * 3 + 2];
+                } else {
+                    const double w0 = L[r].v[0] * (male[r] ? pr.m[0] : pr.a[0]);
+                    const double w1 = L[r].v[1] * (male[r] ? pr.m[1] : pr.a[1]);
+                    const double w2 = L[r].v[2] * (male[r] ? pr.m[2] : pr.a[2]);
+                    div3(w0, w1, w2, (w0 + w1) + w2, p0, p1, p2);
+                }
+                out.put(col[r], p0, p1, p2);
+            }
+        } else if ((flag >> 1) & 1u) {
+            failed = peel<NC, true>(P, pr, L, W[0], W[1], col, out);
+        } else {
+            failed = peel<NC, false>(P, pr, L, W[0], W[1], col, out);
+        }
+    }
+    if (failed) { // the reference returns false: every sample of the variant is reported as NA
+        const int S = C.s;
+        for (int k = 0; k < 3 * S; k++) {
+            post_row[k] = 0.0;
+            if (SINGLE) single_row[k] = 0.0;
+        }
+        for (int c = 0; c < S; c++) gt_row[c] = 255;
+    }
+    *status = failed ? 1 : 0;
 }
 
-template <int NC, int TB>
-__global__ void __launch_bounds__(TB) es_nuclear_kernel(const __grid_constant__ NuclearParams P, const BatchPtrs B) {
+// PL = compact input (uint16 Phred-scaled likelihoods + decode table), SINGLE = the caller wants the individual-only
+// posteriors too (B.single != nullptr).
+template <int NC, int TB, bool PL, bool SINGLE>
+__global__ void __launch_bounds__(TB, NC == 1 ? 896 / TB : 1) es_nuclear_kernel(const __grid_constant__ NuclearParams P, const BatchPtrs B) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    using In = typename std::conditional<PL, uint16_t, double>::type;
     const RunConstants &C = P.C;
     const int S = C.s, S3 = 3 * S;
-    double *s_in = reinterpret_cast<double *>(smem_raw); // [TB][S][3]
-    double *s_post = s_in + TB * S3;
-    double *s_single = s_post + TB * S3;
-    uint8_t *s_gt = reinterpret_cast<uint8_t *>(s_single + TB * S3); // [TB][S]
-    uint8_t *s_status = s_gt + ((TB * S + 15) & ~15);                 // [TB]
+    const unsigned out_bytes = (unsigned)(TB * S3 * sizeof(double));
+    const unsigned in_bytes = (unsigned)(TB * S3 * sizeof(In)); // 192 S (PL) or 768 S bytes per 32 variants: a multiple of 16
+    double *s_post = reinterpret_cast<double *>(smem_raw); // [TB][S][3]
+    double *s_single = s_post + (SINGLE ? TB * S3 : 0);
+    In *s_in = reinterpret_cast<In *>(s_single + TB * S3);                           // [TB][S][3]
+    uint8_t *s_gt = reinterpret_cast<uint8_t *>(s_in) + ((in_bytes + 15u) & ~15u); // [TB][S]
+    uint8_t *s_status = s_gt + ((TB * S + 15) & ~15);                              // [TB]
     __shared__ uint64_t bar;
 
     const int tid = threadIdx.x;
     const int64_t v0 = (int64_t)blockIdx.x * TB;
     const int nv = (int)min((int64_t)TB, B.V - v0);
     const bool full = nv == TB; // full tiles go through TMA; the ragged last tile uses plain loads/stores
-    const unsigned tile_bytes = (unsigned)(TB * S3 * sizeof(double));
+    const In *g_in = (PL ? reinterpret_cast<const In *>(B.pl) : reinterpret_cast<const In *>(B.lk)) + v0 * S3;
 
     if (full) {
         if (tid == 0) mbar_init(&bar, 1);
         __syncthreads();
         if (tid == 0) {
-            mbar_expect_tx(&bar, tile_bytes);
-            bulk_load(s_in, B.lk + v0 * S3, tile_bytes, &bar);
+            mbar_expect_tx(&bar, in_bytes);
+            bulk_load(s_in, g_in, in_bytes, &bar);
         }
     } else {
-        for (int k = tid; k < nv * S3; k += TB) s_in[k] = B.lk[v0 * S3 + k];
+        for (int k = tid; k < nv * S3; k += TB) s_in[k] = g_in[k];
     }
     unsigned flag = 0;
     if (tid < nv && B.flags) flag = B.flags[v0 + tid];
-    const VariantPriors pr = select_priors(C, flag);
     if (full)
         mbar_wait(&bar, 0);
     else
         __syncthreads();
 
-    if (tid < nv) variant_thread<NC>(P, pr, flag, tid, s_in, s_post, s_single, s_gt, s_status);
+    if (tid < nv)
+        variant_thread<NC, PL, SINGLE>(P, flag, s_in + tid * S3, B.lut, s_post + tid * S3, s_single + tid * S3, s_gt + tid * S, s_status + tid);
 
     if (full) {
         fence_async_smem(); // make this thread's shared-memory writes visible to the TMA engine
         __syncthreads();
         if (tid == 0) {
-            bulk_store(B.post + v0 * S3, s_post, tile_bytes);
-            bulk_store(B.single + v0 * S3, s_single, tile_bytes);
+            bulk_store(B.post + v0 * S3, s_post, out_bytes);
+            if (SINGLE) bulk_store(B.single + v0 * S3, s_single, out_bytes);
             bulk_store(B.gt + v0 * S, s_gt, (unsigned)(TB * S));
             bulk_store(B.status + v0, s_status, (unsigned)TB);
             bulk_commit_and_wait_read(); // shared memory must stay alive until the engine has read it
@@ -290,37 +344,39 @@ __global__ void __launch_bounds__(TB) es_nuclear_kernel(const __grid_constant__ 
         __syncthreads();
         for (int k = tid; k < nv * S3; k += TB) {
             B.post[v0 * S3 + k] = s_post[k];
-            B.single[v0 * S3 + k] = s_single[k];
+            if (SINGLE) B.single[v0 * S3 + k] = s_single[k];
         }
         for (int k = tid; k < nv * S; k += TB) B.gt[v0 * S + k] = s_gt[k];
         if (tid < nv) B.status[v0 + tid] = s_status[tid];
     }
 }
 
-template <int NC, int TB> cudaError_t launch_nc(const NuclearParams &P, const BatchPtrs &B, cudaStream_t stream) {
+template <int NC, int TB, bool PL, bool SINGLE> cudaError_t launch_io(const NuclearParams &P, const BatchPtrs &B, cudaStream_t stream) {
     const size_t S = (size_t)P.C.s;
-    const size_t smem = 3 * TB * S * 3 * sizeof(double) + ((TB * S + 15) & ~(size_t)15) + TB;
-    cudaError_t rc = cudaFuncSetAttribute(es_nuclear_kernel<NC, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t in_bytes = (TB * S * 3 * (PL ? sizeof(uint16_t) : sizeof(double)) + 15) & ~(size_t)15;
+    const size_t smem = (SINGLE ? 2 : 1) * TB * S * 3 * sizeof(double) + in_bytes + ((TB * S + 15) & ~(size_t)15) + TB;
+    cudaError_t rc = cudaFuncSetAttribute(es_nuclear_kernel<NC, TB, PL, SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) return rc;
     const unsigned grid = (unsigned)((B.V + TB - 1) / TB);
-    es_nuclear_kernel<NC, TB><<<grid, TB, smem, stream>>>(P, B);
+    es_nuclear_kernel<NC, TB, PL, SINGLE><<<grid, TB, smem, stream>>>(P, B);
     return cudaGetLastError();
+}
+
+template <int NC, int TB> cudaError_t launch_nc(const NuclearParams &P, const BatchPtrs &B, cudaStream_t stream) {
+    if (B.pl) return B.single ? launch_io<NC, TB, true, true>(P, B, stream) : launch_io<NC, TB, true, false>(P, B, stream);
+    return B.single ? launch_io<NC, TB, false, true>(P, B, stream) : launch_io<NC, TB, false, false>(P, B, stream);
 }
 
 } // namespace
 
+// Variants per block (= per TMA tile).  Measured on the trio (profiles/es_tb_check.sh), fraction of the HBM peak:
+// 32 -> 0.946, 64 -> 0.933, 128 -> 0.904, 256 -> 0.72: many one-warp blocks per SM interleave their load / compute /
+// store phases best.  A persistent, double-buffered variant (one block per slot looping over tiles, next tile
+// requested before the current one is computed) was slower (0.854): its barriers serialise what the block
+// scheduler overlaps for free.  P.tb comes from the engine (FAMSEQ_ES_TB, read once in fs_create).
 cudaError_t launch_es_nuclear(const NuclearParams &P, const BatchPtrs &B, cudaStream_t stream) {
     if (B.V <= 0) return cudaSuccess;
-    // Variants per block (= per TMA tile).  Measured on the trio (profiles/es_tb_check.sh), fraction of the HBM peak:
-    // 32 -> 0.946, 64 -> 0.933, 128 -> 0.904, 256 -> 0.72: many one-warp blocks per SM interleave their load / compute /
-    // store phases best.  A persistent, double-buffered variant (one block per slot looping over tiles, next tile
-    // requested before the current one is computed) was slower (0.854): its barriers serialise what the block
-    // scheduler overlaps for free.
-    static const int tb = [] {
-        const char *env = std::getenv("FAMSEQ_ES_TB");
-        return env ? std::atoi(env) : 32;
-    }();
-    switch (P.n_children * 1000 + tb) {
+    switch (P.n_children * 1000 + P.tb) {
     case 1032: return launch_nc<1, 32>(P, B, stream);
     case 2032: return launch_nc<2, 32>(P, B, stream);
     case 3032: return launch_nc<3, 32>(P, B, stream);
@@ -331,11 +387,6 @@ cudaError_t launch_es_nuclear(const NuclearParams &P, const BatchPtrs &B, cudaSt
     case 3064: return launch_nc<3, 64>(P, B, stream);
     case 4064: return launch_nc<4, 64>(P, B, stream);
     case 5064: return launch_nc<5, 64>(P, B, stream);
-    case 1128: return launch_nc<1, 128>(P, B, stream);
-    case 2128: return launch_nc<2, 128>(P, B, stream);
-    case 3128: return launch_nc<3, 128>(P, B, stream);
-    case 4128: return launch_nc<4, 128>(P, B, stream);
-    case 5128: return launch_nc<5, 128>(P, B, stream);
     default: return cudaErrorInvalidValue;
     }
 }

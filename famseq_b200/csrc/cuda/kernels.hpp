@@ -29,8 +29,9 @@ struct NuclearParams {
     int32_t col_father, col_mother;               // input column or -1
     int32_t col_child[ES_NUCLEAR_MAX_CHILDREN];   // children in ped order
     int32_t male_child[ES_NUCLEAR_MAX_CHILDREN];
-    int32_t io_probe; // FAMSEQ_ES_IO_PROBE=1: move the tiles but skip the arithmetic (measures the I/O ceiling; results are garbage)
+    int32_t tb; // variants per block (32 or 64; FAMSEQ_ES_TB, read once in fs_create)
 };
+// Handles B.pl (compact input, decoded through B.lut) and B.single == nullptr itself.
 cudaError_t launch_es_nuclear(const NuclearParams &P, const BatchPtrs &B, cudaStream_t stream);
 
 // ---- Bayesian network (bn_kernel.cu) --------------------------------------------------------------
@@ -48,8 +49,19 @@ struct McmcParams {
 };
 size_t mcmc_smem_bytes(const McmcParams &P, int tb);
 int mcmc_pick_block(const McmcParams &P, size_t smem_limit, size_t smem_per_sm);
-// fixup: only variants whose status byte is 2 are processed (what the specialised kernel of gibbs_jit.cu left over).
+// Launch-time tuning, read from the environment once in fs_create (FAMSEQ_MCMC_BLOCKS, FAMSEQ_MCMC_WGLOBAL).
+struct McmcTuning {
+    int blocks_cap = 3; // resident blocks per SM when the own factors live in L2
+    int wglobal = -1;   // own factors in L2 (1) / shared memory (0) / by pedigree size (-1)
+};
+// fixup: only variants whose status byte is 2 are processed (what the specialised kernel of gibbs_jit.cu left over);
+// *fixup_count (device, may be null) is incremented once per such variant.
 cudaError_t launch_mcmc(const McmcParams &P, const BatchPtrs &B, int tb, int burn, int rep, uint64_t seed,
-                        int64_t v_offset, int sm_count, cudaStream_t stream, bool fixup = false);
+                        int64_t v_offset, int sm_count, cudaStream_t stream, const McmcTuning &tune, bool fixup = false,
+                        unsigned long long *fixup_count = nullptr);
+
+// ---- compact input (engine.cu) ----------------------------------------------------------------------
+// lk[k] = lut[pl[k]] for k < n: expands fs_run_pl input for the kernels that read FP64 likelihoods.
+cudaError_t launch_pl_decode(const uint16_t *pl, const double *lut, double *lk, int64_t n, cudaStream_t stream);
 
 } // namespace famseq

@@ -28,7 +28,6 @@
 //     of a half-warp hit 16 different bank pairs;
 //   * persistent blocks loop over tiles of TB variants.
 #include <algorithm>
-#include <cstdlib>
 
 #include "common.cuh"
 #include "kernels.hpp"
@@ -102,7 +101,8 @@ __device__ __forceinline__ double fast_reciprocal(double s) {
 //                  shared memory then only holds the tables and the number of chains per SM is set by registers.
 template <int TB, bool WGLOBAL, int GW>
 __global__ void __launch_bounds__(TB) mcmc_kernel(const __grid_constant__ McmcParams P, const BatchPtrs B, int burn, int rep,
-                                                  uint64_t seed, int64_t v_offset, double *__restrict__ scratch, int n_tiles, int fixup) {
+                                                  uint64_t seed, int64_t v_offset, double *__restrict__ scratch, int n_tiles, int fixup,
+                                                  unsigned long long *fixup_count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const RunConstants &C = P.C;
     const McmcPlan &pl = P.plan;
@@ -126,7 +126,10 @@ __global__ void __launch_bounds__(TB) mcmc_kernel(const __grid_constant__ McmcPa
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t v = (int64_t)tile * TB + tid;
         if (v >= B.V) continue;
-        if (fixup && B.status[v] != 2) continue; // second pass after the specialised kernel: only what it left (status 2)
+        if (fixup) { // second pass after the specialised kernel: only what it left (status 2)
+            if (B.status[v] != 2) continue;
+            if (fixup_count) atomicAdd(fixup_count, 1ull);
+        }
         const unsigned flag = B.flags ? B.flags[v] : 0u;
         const bool chrx = (flag >> 1) & 1u;
         const VariantPriors pr = select_priors(C, flag);
@@ -311,7 +314,7 @@ __global__ void __launch_bounds__(TB) mcmc_kernel(const __grid_constant__ McmcPa
 
 template <int TB, bool WGLOBAL, int GW = 2>
 cudaError_t launch_tb(const McmcParams &P, const BatchPtrs &B, int burn, int rep, uint64_t seed, int64_t v_offset, int sm_count,
-                      cudaStream_t stream, bool fixup) {
+                      cudaStream_t stream, int blocks_cap, bool fixup, unsigned long long *fixup_count) {
     const size_t smem = WGLOBAL ? (size_t)kEntries * kCopies * sizeof(double) : mcmc_smem_bytes(P, TB);
     cudaError_t rc = cudaFuncSetAttribute(mcmc_kernel<TB, WGLOBAL, GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) return rc;
@@ -320,9 +323,7 @@ cudaError_t launch_tb(const McmcParams &P, const BatchPtrs &B, int burn, int rep
     if (rc != cudaSuccess) return rc;
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
     if (WGLOBAL) { // resident blocks per SM (measured on ped40: 1 -> 1.60e5, 2 -> 1.63e5, 3 -> 1.79e5 variants/s)
-        int cap = 3;
-        if (const char *env = std::getenv("FAMSEQ_MCMC_BLOCKS")) cap = std::max(1, std::atoi(env));
-        per_sm = std::min(per_sm, cap);
+        per_sm = std::min(per_sm, std::max(1, blocks_cap));
     }
     const int64_t n_tiles = (B.V + TB - 1) / TB;
     if (n_tiles > 0x7fffffff) return cudaErrorInvalidValue;
@@ -331,7 +332,8 @@ cudaError_t launch_tb(const McmcParams &P, const BatchPtrs &B, int burn, int rep
     double *scratch = nullptr;
     rc = cudaMallocAsync(&scratch, (size_t)grid * P.plan.n * 3 * TB * sizeof(double) * (WGLOBAL ? 2 : 1), stream);
     if (rc != cudaSuccess) return rc;
-    mcmc_kernel<TB, WGLOBAL, GW><<<grid, TB, smem, stream>>>(P, B, burn, rep, seed, v_offset, scratch, (int)n_tiles, fixup ? 1 : 0);
+    mcmc_kernel<TB, WGLOBAL, GW><<<grid, TB, smem, stream>>>(P, B, burn, rep, seed, v_offset, scratch, (int)n_tiles, fixup ? 1 : 0,
+                                                           fixup_count);
     rc = cudaGetLastError();
     const cudaError_t rc2 = cudaFreeAsync(scratch, stream);
     return rc != cudaSuccess ? rc : rc2;
@@ -358,22 +360,21 @@ int mcmc_pick_block(const McmcParams &P, size_t smem_limit, size_t smem_per_sm) 
 }
 
 cudaError_t launch_mcmc(const McmcParams &P, const BatchPtrs &B, int tb, int burn, int rep, uint64_t seed, int64_t v_offset,
-                        int sm_count, cudaStream_t stream, bool fixup) {
+                        int sm_count, cudaStream_t stream, const McmcTuning &tune, bool fixup, unsigned long long *fixup_count) {
     if (B.V <= 0) return cudaSuccess;
     // Large pedigrees: the own factors of fewer than 512 chains fit in an SM's shared memory -> keep them in L2 instead.
-    bool wglobal = tb < 256;
-    if (const char *env = std::getenv("FAMSEQ_MCMC_WGLOBAL")) wglobal = env[0] == '1';
-    if (P.plan.n > 64) return launch_tb<256, true, 4>(P, B, burn, rep, seed, v_offset, sm_count, stream, fixup); // wide genotype vector
-    if (wglobal) return launch_tb<256, true>(P, B, burn, rep, seed, v_offset, sm_count, stream, fixup);
+    const bool wglobal = tune.wglobal < 0 ? tb < 256 : tune.wglobal != 0;
+    if (P.plan.n > 64) return launch_tb<256, true, 4>(P, B, burn, rep, seed, v_offset, sm_count, stream, tune.blocks_cap, fixup, fixup_count); // wide genotype vector
+    if (wglobal) return launch_tb<256, true>(P, B, burn, rep, seed, v_offset, sm_count, stream, tune.blocks_cap, fixup, fixup_count);
     switch (tb) {
-    case 256: return launch_tb<256, false>(P, B, burn, rep, seed, v_offset, sm_count, stream, fixup);
-    case 224: return launch_tb<224, false>(P, B, burn, rep, seed, v_offset, sm_count, stream, fixup);
-    case 192: return launch_tb<192, false>(P, B, burn, rep, seed, v_offset, sm_count, stream, fixup);
-    case 160: return launch_tb<160, false>(P, B, burn, rep, seed, v_offset, sm_count, stream, fixup);
-    case 128: return launch_tb<128, false>(P, B, burn, rep, seed, v_offset, sm_count, stream, fixup);
-    case 96: return launch_tb<96, false>(P, B, burn, rep, seed, v_offset, sm_count, stream, fixup);
-    case 64: return launch_tb<64, false>(P, B, burn, rep, seed, v_offset, sm_count, stream, fixup);
-    case 32: return launch_tb<32, false>(P, B, burn, rep, seed, v_offset, sm_count, stream, fixup);
+    case 256: return launch_tb<256, false>(P, B, burn, rep, seed, v_offset, sm_count, stream, tune.blocks_cap, fixup, fixup_count);
+    case 224: return launch_tb<224, false>(P, B, burn, rep, seed, v_offset, sm_count, stream, tune.blocks_cap, fixup, fixup_count);
+    case 192: return launch_tb<192, false>(P, B, burn, rep, seed, v_offset, sm_count, stream, tune.blocks_cap, fixup, fixup_count);
+    case 160: return launch_tb<160, false>(P, B, burn, rep, seed, v_offset, sm_count, stream, tune.blocks_cap, fixup, fixup_count);
+    case 128: return launch_tb<128, false>(P, B, burn, rep, seed, v_offset, sm_count, stream, tune.blocks_cap, fixup, fixup_count);
+    case 96: return launch_tb<96, false>(P, B, burn, rep, seed, v_offset, sm_count, stream, tune.blocks_cap, fixup, fixup_count);
+    case 64: return launch_tb<64, false>(P, B, burn, rep, seed, v_offset, sm_count, stream, tune.blocks_cap, fixup, fixup_count);
+    case 32: return launch_tb<32, false>(P, B, burn, rep, seed, v_offset, sm_count, stream, tune.blocks_cap, fixup, fixup_count);
     default: return cudaErrorInvalidValue;
     }
 }

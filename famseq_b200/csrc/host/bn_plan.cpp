@@ -3,7 +3,8 @@
 #include <cstring>
 
 #include "../../../include/famseq_b200.h"
-#include "bn_planner.hpp"
+#include "bn_plan.hpp"
+#include "pedigree.hpp"
 
 namespace famseq {
 

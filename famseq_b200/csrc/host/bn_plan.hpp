@@ -13,8 +13,11 @@
 #pragma once
 
 #include <cstdint>
+#include <string>
 
 namespace famseq {
+
+struct Pedigree; // host/pedigree.hpp
 
 constexpr int BN_MAX_LEVELS = 31; // 2 bits per level in a 64-bit word, field 31 stays zero
 constexpr int BN_MAX_UNROLL = 5;
@@ -46,5 +49,8 @@ struct BnPlan {
     // unrolled block's table rows must be re-read only when a rolled level <= this one changes
     int32_t unrolled_dep = -1;
 };
+
+// Host entry point (bn_plan.cpp): builds the enumeration plan.  Returns FS_OK or FS_E_TOO_LARGE.
+int build_bn_plan(const Pedigree &ped, BnPlan &out, std::string &err);
 
 } // namespace famseq

@@ -7,7 +7,8 @@
 // (family.cpp:1609-1646, :1817-1843, :1292-1303) so that the kernel, which is compiled without FMA
 // contraction, reproduces the reference's doubles bit for bit.  Multiplications by an exact 1.0
 // (unsequenced members, empty spouse products) are dropped -- they cannot change a double.
-#include "es_compiler.hpp"
+#include "es_program.hpp"
+#include "pedigree.hpp"
 
 #include <algorithm>
 #include <map>

@@ -7,6 +7,7 @@
 #pragma once
 
 #include <cstdint>
+#include <string>
 
 #ifdef __CUDACC__
 #define FS_HD __host__ __device__
@@ -15,6 +16,8 @@
 #endif
 
 namespace famseq {
+
+struct Pedigree; // host/pedigree.hpp
 
 // Inside the compiler a "vector reference" names a genotype 3-vector by kind and index.  In the encoded program an
 // operand is a 16-bit index into the per-variant VECTOR FILE the kernel keeps in shared memory:
@@ -62,5 +65,9 @@ struct EsProgram {
     int32_t n_cols = 0;
     uint32_t words[ES_MAX_WORDS];
 };
+
+// Host entry point of the pedigree compiler (es_program.cpp).  Returns FS_OK, FS_E_LOOP (pedigree is not
+// peelable) or FS_E_TOO_LARGE; `err` receives the text.
+int compile_es_program(const Pedigree &ped, EsProgram &out, std::string &err);
 
 } // namespace famseq

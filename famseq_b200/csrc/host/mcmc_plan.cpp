@@ -1,6 +1,7 @@
 // mcmc_plan.cpp -- see mcmc_plan.hpp.
 #include "../../../include/famseq_b200.h"
-#include "mcmc_planner.hpp"
+#include "mcmc_plan.hpp"
+#include "pedigree.hpp"
 
 namespace famseq {
 

@@ -6,8 +6,11 @@
 #pragma once
 
 #include <cstdint>
+#include <string>
 
 namespace famseq {
+
+struct Pedigree; // host/pedigree.hpp
 
 constexpr int MCMC_MAX_MEMBERS = 128; // genotype vector packed 2 bits/member in two (<= 64 members) or four 64-bit registers
 constexpr int MCMC_MAX_LINKS = 255;
@@ -21,5 +24,8 @@ struct McmcPlan {
     uint16_t link[MCMC_MAX_LINKS + 1];
     int16_t col[MCMC_MAX_MEMBERS]; // input column or -1
 };
+
+// Host entry point (mcmc_plan.cpp): builds the neighbour lists.  Returns FS_OK or FS_E_TOO_LARGE.
+int build_mcmc_plan(const Pedigree &ped, McmcPlan &out, std::string &err);
 
 } // namespace famseq

@@ -60,7 +60,10 @@ class Params(ctypes.Structure):
 class _Info(ctypes.Structure):
     _fields_ = [(k, ctypes.c_int32) for k in ("n", "s", "n_founders", "has_loop", "es_ops", "es_slots", "bn_levels",
                                                "bn_group", "mcmc_links", "device")] + [("kernel_launches", ctypes.c_int64),
-                                                                                      ("jit_launches", ctypes.c_int64)]
+                                                                                      ("jit_launches", ctypes.c_int64),
+                                                                                      ("mcmc_fixups", ctypes.c_int64),
+                                                                                      ("n_devices", ctypes.c_int32),
+                                                                                      ("reserved", ctypes.c_int32)]
 
 
 _lib = None
@@ -80,6 +83,14 @@ def lib() -> ctypes.CDLL:
         L.fs_device_count.restype = ctypes.c_int
         L.fs_create.restype = ctypes.c_int
         L.fs_create.argtypes = [P, P, ctypes.c_int, P]
+        L.fs_create_multi.restype = ctypes.c_int
+        L.fs_create_multi.argtypes = [P, P, P, ctypes.c_int, P]
+        L.fs_run_pl.restype = ctypes.c_int
+        L.fs_run_pl.argtypes = [P, ctypes.c_int, I64, P, P, I32, I32, U64, I64, P, P, P, P]
+        L.fs_run_pl_device.restype = ctypes.c_int
+        L.fs_run_pl_device.argtypes = [P, ctypes.c_int, I64, P, P, I32, I32, U64, I64, P, P, P, P, P]
+        L.fs_get_pl_table.restype = ctypes.c_int
+        L.fs_get_pl_table.argtypes = [P, P]
         L.fs_destroy.restype = None
         L.fs_destroy.argtypes = [P]
         L.fs_last_error.restype = ctypes.c_char_p
@@ -107,7 +118,8 @@ def lib() -> ctypes.CDLL:
 
 EXPORTED_SYMBOLS = ["fs_default_params", "fs_device_count", "fs_create", "fs_destroy", "fs_last_error", "fs_run",
                     "fs_run_device", "fs_get_info", "fs_get_tables", "fs_alloc_pinned", "fs_free_pinned",
-                    "fs_last_kernel_ms", "fs_bench_fp64_tflops", "fs_get_es_program", "fs_get_gibbs_kernel", "fs_get_es_kernel", "fs_warmup"]
+                    "fs_last_kernel_ms", "fs_bench_fp64_tflops", "fs_get_es_program", "fs_get_gibbs_kernel", "fs_get_es_kernel", "fs_warmup",
+                    "fs_create_multi", "fs_run_pl", "fs_run_pl_device", "fs_get_pl_table"]
 
 
 def _check(rc: int) -> None:
@@ -136,16 +148,21 @@ class Result:
 
 
 class Engine:
-    """One pedigree compiled for one GPU (fs_create / fs_destroy)."""
+    """One pedigree compiled for one GPU (fs_create) or, with `device` a list of GPUs, for several (fs_create_multi:
+    every batch call is cut into one contiguous slice of variants per GPU)."""
 
-    def __init__(self, ids, mother_ids, father_ids, genders, cols, params: Params | None = None, device: int = 0):
+    def __init__(self, ids, mother_ids, father_ids, genders, cols, params: Params | None = None, device=0):
         self._h = ctypes.c_void_p()
         self._keep = [_i32(ids), _i32(mother_ids), _i32(father_ids), _i32(genders), _i32(cols)]
         ped = _Pedigree(len(self._keep[0]), _ptr(self._keep[0]), _ptr(self._keep[1]), _ptr(self._keep[2]),
                         _ptr(self._keep[3]), len(self._keep[4]), _ptr(self._keep[4]))
         self.params = params if params is not None else Params.default()
         self.device = device
-        _check(lib().fs_create(ctypes.byref(ped), ctypes.byref(self.params), device, ctypes.byref(self._h)))
+        if isinstance(device, (list, tuple)):
+            devs = _i32(list(device))
+            _check(lib().fs_create_multi(ctypes.byref(ped), ctypes.byref(self.params), _ptr(devs), len(devs), ctypes.byref(self._h)))
+        else:
+            _check(lib().fs_create(ctypes.byref(ped), ctypes.byref(self.params), device, ctypes.byref(self._h)))
         self.n, self.s = ped.n, ped.s
 
     def close(self) -> None:
@@ -211,25 +228,40 @@ class Engine:
         _check(f(self._h, 1 if compile else 0, buf, len(buf), ctypes.byref(n), ctypes.byref(cb)))
         return buf.value.decode("utf-8", "replace"), int(cb.value)
 
+    def pl_table(self) -> np.ndarray:
+        """The 65 536-entry PL decode table of fs_run_pl (built on the host with libm's pow)."""
+        out = np.empty(65536, np.float64)
+        _check(lib().fs_get_pl_table(self._h, _ptr(out)))
+        return out
+
     def last_kernel_ms(self) -> float:
         return float(lib().fs_last_kernel_ms(self._h))
 
     # -- batch calls on host buffers ------------------------------------------------------------------
     def run(self, method: int, lk, flags=None, burn: int = 1000, rep: int = 100000, seed: int = 0,
-            v_offset: int = 0, out: Result | None = None) -> Result:
-        lk = np.ascontiguousarray(lk, dtype=np.float64)
-        if lk.ndim != 3 or lk.shape[1] != self.s or lk.shape[2] != 3:
-            raise ValueError(f"lk must be [V][{self.s}][3]")
-        V = lk.shape[0]
+            v_offset: int = 0, out: Result | None = None, want_single: bool = True) -> Result:
+        """fs_run on numpy arrays.  want_single=False passes single = NULL (Result.single is then None)."""
+        return self._run_host("fs_run", np.float64, method, lk, flags, burn, rep, seed, v_offset, out, want_single)
+
+    def run_pl(self, method: int, pl, flags=None, burn: int = 1000, rep: int = 100000, seed: int = 0,
+               v_offset: int = 0, out: Result | None = None, want_single: bool = True) -> Result:
+        """fs_run_pl: compact input, pl[V][S][3] uint16 Phred-scaled likelihoods (lk = 10^(-pl/10), file.cpp:588-590)."""
+        return self._run_host("fs_run_pl", np.uint16, method, pl, flags, burn, rep, seed, v_offset, out, want_single)
+
+    def _run_host(self, symbol, dtype, method, x, flags, burn, rep, seed, v_offset, out, want_single) -> Result:
+        x = np.ascontiguousarray(x, dtype=dtype)
+        if x.ndim != 3 or x.shape[1] != self.s or x.shape[2] != 3:
+            raise ValueError(f"input must be [V][{self.s}][3]")
+        V = x.shape[0]
         if flags is not None:
             flags = np.ascontiguousarray(flags, dtype=np.uint8)
             if flags.shape != (V,):
                 raise ValueError("flags must be [V]")
         if out is None:
-            out = Result(np.empty((V, self.s, 3)), np.empty((V, self.s, 3)), np.empty((V, self.s), np.uint8),
-                         np.empty(V, np.uint8))
-        _check(lib().fs_run(self._h, method, V, _ptr(lk), _ptr(flags), burn, rep, seed, v_offset, _ptr(out.post),
-                            _ptr(out.single), _ptr(out.gt), _ptr(out.status)))
+            out = Result(np.empty((V, self.s, 3)), np.empty((V, self.s, 3)) if want_single else None,
+                         np.empty((V, self.s), np.uint8), np.empty(V, np.uint8))
+        _check(getattr(lib(), symbol)(self._h, method, V, _ptr(x), _ptr(flags), burn, rep, seed, v_offset, _ptr(out.post),
+                                      _ptr(out.single), _ptr(out.gt), _ptr(out.status)))
         return out
 
     def run_raw(self, method: int, V: int, lk_ptr, flags_ptr, post_ptr, single_ptr, gt_ptr, status_ptr, burn=1000,
@@ -237,6 +269,19 @@ class Engine:
         """fs_run on raw HOST addresses (e.g. pinned torch tensors)."""
         _check(lib().fs_run(self._h, method, V, _ptr(lk_ptr), _ptr(flags_ptr), burn, rep, seed, v_offset, _ptr(post_ptr),
                             _ptr(single_ptr), _ptr(gt_ptr), _ptr(status_ptr)))
+
+    def run_pl_raw(self, method: int, V: int, pl_ptr, flags_ptr, post_ptr, single_ptr, gt_ptr, status_ptr, burn=1000,
+                   rep=100000, seed=0, v_offset=0) -> None:
+        """fs_run_pl on raw HOST addresses; single_ptr may be None."""
+        _check(lib().fs_run_pl(self._h, method, V, _ptr(pl_ptr), _ptr(flags_ptr), burn, rep, seed, v_offset, _ptr(post_ptr),
+                               _ptr(single_ptr), _ptr(gt_ptr), _ptr(status_ptr)))
+
+    def run_pl_device(self, method: int, V: int, pl_ptr, flags_ptr, post_ptr, single_ptr, gt_ptr, status_ptr, burn=1000,
+                      rep=100000, seed=0, v_offset=0, stream=0) -> None:
+        """fs_run_pl_device on raw DEVICE addresses; asynchronous on `stream`; single_ptr may be None."""
+        _check(lib().fs_run_pl_device(self._h, method, V, _ptr(pl_ptr), _ptr(flags_ptr), burn, rep, seed, v_offset,
+                                      _ptr(post_ptr), _ptr(single_ptr), _ptr(gt_ptr), _ptr(status_ptr),
+                                      ctypes.c_void_p(int(stream))))
 
     def run_device(self, method: int, V: int, lk_ptr, flags_ptr, post_ptr, single_ptr, gt_ptr, status_ptr, burn=1000,
                    rep=100000, seed=0, v_offset=0, stream=0) -> None:

@@ -37,10 +37,15 @@ def gather_to_rank0(dist, array, n_variants: int):
 
     world, rank = dist.get_world_size(), dist.get_rank()
     sizes = [shard_range(n_variants, r, world) for r in range(world)]
-    mine = torch.from_numpy(np.ascontiguousarray(array))
+    # dist.gather needs equally sized tensors: pad every slice to the largest one, trim on rank 0
+    rows = max(hi - lo for lo, hi in sizes)
+    mine = np.ascontiguousarray(array)
+    padded = np.zeros((rows,) + mine.shape[1:], dtype=mine.dtype)
+    padded[:mine.shape[0]] = mine
+    mine_t = torch.from_numpy(padded)
     if rank == 0:
-        parts = [torch.empty((hi - lo,) + tuple(mine.shape[1:]), dtype=mine.dtype) for lo, hi in sizes]
-        dist.gather(mine, parts, dst=0)
-        return np.concatenate([p.numpy() for p in parts])
-    dist.gather(mine, None, dst=0)
+        parts = [torch.empty_like(mine_t) for _ in sizes]
+        dist.gather(mine_t, parts, dst=0)
+        return np.concatenate([p.numpy()[:hi - lo] for p, (lo, hi) in zip(parts, sizes)])
+    dist.gather(mine_t, None, dst=0)
     return None

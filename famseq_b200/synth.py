@@ -11,6 +11,8 @@ from __future__ import annotations
 
 from dataclasses import dataclass, field
 
+import math
+
 import numpy as np
 
 CHUNK = 65536
@@ -279,9 +281,21 @@ def synth_pl(ped: PedFile, n_variants: int, seed: int, v0: int = 0, x_fraction: 
     return np.concatenate(pls), np.concatenate(fls)
 
 
+_PL_TABLE = None
+
+
+def pl_table() -> np.ndarray:
+    """pow(10, -pl/10) for pl = 0..65535 evaluated by libm (math.pow), like the reference's VCF driver and like the
+    engine's fs_run_pl decode table; numpy's own power() differs from libm in the last bit for ~0.2 % of these."""
+    global _PL_TABLE
+    if _PL_TABLE is None:
+        _PL_TABLE = np.array([math.pow(10.0, -abs(float(k)) / 10.0) for k in range(65536)], dtype=np.float64)
+    return _PL_TABLE
+
+
 def pl_to_likelihood(pl: np.ndarray) -> np.ndarray:
-    """The VCF driver's decode: pow(10, -|PL|/10) (file.cpp:588-590)."""
-    return np.power(10.0, -np.abs(pl.astype(np.float64)) / 10.0)
+    """The VCF driver's decode: pow(10, -|PL|/10) (file.cpp:588-590); integer PLs beyond 65535 decode to 0 anyway."""
+    return pl_table()[np.minimum(np.abs(pl.astype(np.int64)), 65535)]
 
 
 def synth_likelihoods(ped: PedFile, n_variants: int, seed: int, v0: int = 0, x_fraction: float = 0.0):

@@ -21,6 +21,9 @@
  *   get_postProb(true)            family.cpp:576-604      post[V][S][3]
  *   get_postProbSingle(true)      family.cpp:606-634      single[V][S][3]
  *   get_postRlt()                 family.cpp:636-665      gt[V][S]  (0,1,2; 255 = the reference's -1)
+ *   pow(10, -fabs(PL)/10)         file.cpp:588-590,       fs_run_pl(..., uint16 pl[V][S][3], ...): the caller ships
+ *     (the VCF driver's decode)     :825-827                the integer PL fields, the device decodes them through
+ *                                                           a table built on the host with the same libm call
  *
  * All entry points are plain C: pointers and sizes only.  Every function returns FS_OK (0) or a
  * negative FS_E_* code; fs_last_error() returns a thread-local message for the last failure.
@@ -36,7 +39,7 @@
 extern "C" {
 #endif
 
-#define FS_ABI_VERSION 1
+#define FS_ABI_VERSION 2
 
 enum fs_method { FS_METHOD_BN = 1, FS_METHOD_ES = 2, FS_METHOD_MCMC = 3 }; /* the CLI's -method 1|2|3 */
 
@@ -91,6 +94,13 @@ int fs_device_count(void);
 int fs_create(const fs_pedigree *ped, const fs_params *params, int device, fs_engine **out);
 void fs_destroy(fs_engine *e);
 
+/* One engine that drives `ndev` GPUs: the pedigree program is replicated, every fs_run /
+ * fs_run_pl call is cut into `ndev` contiguous slices of variants -- slice g = [g V/ndev, (g+1) V/ndev) on devices[g],
+ * one host thread and one copy/compute pipeline per GPU -- and every GPU writes its slice of the caller's ordered
+ * host buffers.  There is no inter-GPU collective; Gibbs streams are keyed by the global variant index, so the bytes
+ * do not depend on ndev.  The *_device entry points need a single-GPU engine (FS_E_ARG otherwise). */
+int fs_create_multi(const fs_pedigree *ped, const fs_params *params, const int *devices, int ndev, fs_engine **out);
+
 /* Thread-local text of the last error raised on the calling thread. */
 const char *fs_last_error(void);
 
@@ -101,7 +111,10 @@ const char *fs_last_error(void);
  *   seed, v_offset    Philox key and global index of variant 0: variant v draws from the stream
  *                     keyed (seed, v_offset + v), so any sharding of the input gives identical bytes
  *   post, single [V][S][3], gt [V][S], status [V]   outputs (see the table above)
- * The call is internally pipelined (H2D / kernel / D2H on separate streams). */
+ *   single may be NULL: the individual-only posteriors are then neither stored nor copied back (a caller can
+ *   recompute them from the likelihoods alone: single = lk * prior / sum, family.cpp:1405-1499)
+ * The call is internally pipelined (H2D / kernel / D2H on separate streams).  On any error every copy already
+ * queued into the caller's buffers has completed before the call returns. */
 int fs_run(fs_engine *e, int method, int64_t V, const double *lk, const uint8_t *flags, int32_t burn,
            int32_t rep, uint64_t seed, int64_t v_offset, double *post, double *single, uint8_t *gt,
            uint8_t *status);
@@ -111,6 +124,22 @@ int fs_run(fs_engine *e, int method, int64_t V, const double *lk, const uint8_t 
 int fs_run_device(fs_engine *e, int method, int64_t V, const double *d_lk, const uint8_t *d_flags, int32_t burn,
                   int32_t rep, uint64_t seed, int64_t v_offset, double *d_post, double *d_single,
                   uint8_t *d_gt, uint8_t *d_status, void *stream);
+
+/* Compact input (input half).  The reference's VCF driver turns every PL (or GL) field x
+ * into the likelihood pow(10, -fabs(x)/10) (file.cpp:588-590, :825-827).  For the usual integer PL fields the caller
+ * can ship the integers themselves: pl[V][S][3], uint16, 2 bytes per value instead of 8.  The engine decodes them on
+ * the device through a 65 536-entry table that fs_create fills ON THE HOST with exactly that libm expression, so the
+ * likelihoods -- and therefore every output byte -- are identical to fs_run on the decoded doubles.  Values above
+ * 65 535 may be clamped to 65 535 by the caller (every PL >= 3240 decodes to exactly 0.0); missing samples are
+ * (0, 0, 0) = likelihood (1, 1, 1) (file.cpp:802-811).  Non-integer or GL input takes fs_run.  `single` may be NULL. */
+int fs_run_pl(fs_engine *e, int method, int64_t V, const uint16_t *pl, const uint8_t *flags, int32_t burn, int32_t rep,
+              uint64_t seed, int64_t v_offset, double *post, double *single, uint8_t *gt, uint8_t *status);
+int fs_run_pl_device(fs_engine *e, int method, int64_t V, const uint16_t *d_pl, const uint8_t *d_flags, int32_t burn,
+                     int32_t rep, uint64_t seed, int64_t v_offset, double *d_post, double *d_single, uint8_t *d_gt,
+                     uint8_t *d_status, void *stream);
+/* Copies the decode table (65 536 doubles) the engine uses; works on host-only engines (tests compare it with libm). */
+int fs_get_pl_table(const fs_engine *e, double *out);
+#define FS_PL_TABLE_SIZE 65536
 
 /* Introspection of the compiled pedigree program (all fields are counts). */
 typedef struct fs_info {
@@ -124,7 +153,11 @@ typedef struct fs_info {
     int32_t mcmc_links;       /* parent-child links visited per Gibbs sweep                           */
     int32_t device;           /* CUDA device or -1                                                    */
     int64_t kernel_launches;  /* kernels launched by this engine so far                               */
-    int64_t jit_launches;     /* ... of which launches of the run-time compiled Gibbs kernel          */
+    int64_t jit_launches;     /* ... of which launches of the run-time compiled Gibbs / ES kernels    */
+    int64_t mcmc_fixups;      /* chains the generated Gibbs kernel handed back (status 2) and the table-driven
+                               * kernel redid; read from the device, so only exact once the work has completed */
+    int32_t n_devices;        /* GPUs behind this engine (fs_create_multi), 1 for fs_create, 0 host-only        */
+    int32_t reserved;
 } fs_info;
 int fs_get_info(const fs_engine *e, fs_info *out);
 
@@ -156,7 +189,8 @@ int fs_get_es_kernel(const fs_engine *e, int compile, char *text, size_t capacit
  * input to read can run this on a helper thread first (the command line does) and hide the ~0.3 s it takes. */
 int fs_warmup(int device);
 
-/* Pinned host memory helpers for callers without their own CUDA runtime binding. */
+/* Pinned host memory helpers for callers without their own CUDA runtime binding (portable: usable from every GPU of a
+ * multi-device engine). */
 void *fs_alloc_pinned(size_t bytes);
 void fs_free_pinned(void *p);
 

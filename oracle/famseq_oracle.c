@@ -432,6 +432,13 @@ static inline uint32_t mulhilo(uint32_t a, uint32_t b, uint32_t *hi) {
 }
 
 /* Philox4x32-10 (Salmon et al., SC'11), the same constants as in the CUDA kernel. */
+/* file.cpp:588-590 (= :825-827): lkTmp = atof(field); lkTmp = pow(10.0, -fabs(lkTmp) / 10.0); */
+double fso_pl_decode(double x) { return pow(10.0, -fabs(x) / 10.0); }
+
+void fso_pl_table(double *out, int n) {
+    for (int k = 0; k < n; k++) out[k] = fso_pl_decode((double)k);
+}
+
 void fso_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
     uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
     for (int r = 0; r < 10; r++) {
@@ -492,6 +499,15 @@ static double rng_uniform(rng_t *r, int sweep, int member) {
     return ((double)rng_u32(r, sweep, member) + 0.5) * (1.0 / 4294967296.0);
 }
 
+/* Test probe: smallest and largest weight sum `s` met by the chains of the last fso_run(MCMC) call (all its variants).
+ * The generated CUDA Gibbs kernel hands a chain back to the table-driven kernel when a sum leaves the positive normal
+ * range [2^-963, 2^963); the tests use this probe to check that it does so exactly when it must. */
+static double g_sum_min = 0, g_sum_max = 0;
+void fso_mcmc_sum_range(double out[2]) {
+    out[0] = g_sum_min;
+    out[1] = g_sum_max;
+}
+
 /* one sweep over all individuals in ped order */
 static void gibbs_sweep(const fam_t *f, int *cur, double *acc, int known, int chrx, rng_t *rng, int sweep) {
     const int N = f->N;
@@ -516,6 +532,8 @@ static void gibbs_sweep(const fam_t *f, int *cur, double *acc, int known, int ch
         }
         double s = 0;
         for (int g = 0; g < 3; g++) s = s + w[g];
+        if (!(s >= g_sum_min)) g_sum_min = s; /* NaN sticks */
+        if (!(s <= g_sum_max)) g_sum_max = s;
         if (s <= 0)
             w[0] = w[1] = w[2] = 0;
         else
@@ -583,6 +601,8 @@ int fso_run(int method, int N, const int *ped_id, const int *ped_mid, const int 
     memcpy(f->prior, priors, sizeof(double) * 12);
     fso_tables(mrate, f->tA, f->tXf, f->tXm);
     if (method == FSO_MCMC && rng_kind == FSO_RNG_LIBC && seed >= 0) srand((unsigned)seed);
+    g_sum_min = INFINITY;
+    g_sum_max = -INFINITY;
 
     for (int64_t v = 0; v < V; v++) {
         const int known = flags[v] & 1, chrx = (flags[v] >> 1) & 1;

@@ -57,6 +57,14 @@ int fso_run(int method, int N, const int *ped_id, const int *ped_mid, const int 
 int fso_topology(int N, const int *ped_id, const int *ped_mid, const int *ped_fid, const int *gender,
                  int *mother, int *father);
 
+/* The VCF driver's likelihood decode (file.cpp:588-590, :825-827): pow(10, -fabs(x)/10) of a PL / GL field. */
+double fso_pl_decode(double x);
+/* ... for every integer PL 0 .. n-1 at once (the table the engine's fs_run_pl decodes through). */
+void fso_pl_table(double *out, int n);
+
+/* Test probe: {min, max} of the Gibbs weight sums met during the last fso_run(FSO_MCMC) call (over all its variants). */
+void fso_mcmc_sum_range(double out[2]);
+
 /* Philox4x32-10 block, exposed so the host/CUDA implementations can be checked against it. */
 void fso_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 

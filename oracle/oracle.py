@@ -55,6 +55,12 @@ def lib() -> ctypes.CDLL:
         L.fso_tables.argtypes = [ctypes.c_double, P, P, P]
         L.fso_topology.restype = ctypes.c_int
         L.fso_topology.argtypes = [ctypes.c_int, P, P, P, P, P, P]
+        L.fso_pl_decode.restype = ctypes.c_double
+        L.fso_pl_decode.argtypes = [ctypes.c_double]
+        L.fso_pl_table.restype = None
+        L.fso_pl_table.argtypes = [P, ctypes.c_int]
+        L.fso_mcmc_sum_range.restype = None
+        L.fso_mcmc_sum_range.argtypes = [P]
         L.fso_philox4x32.restype = None
         L.fso_philox4x32.argtypes = [P, P, P]
         _lib = L
@@ -111,6 +117,13 @@ def tables(mrate: float):
     return a, xf, xm
 
 
+def pl_table(n: int = 65536) -> np.ndarray:
+    """pow(10, -fabs(pl)/10) for pl = 0..n-1 (file.cpp:588-590), evaluated by the C restatement (libm)."""
+    out = np.empty(n, np.float64)
+    lib().fso_pl_table(_ptr(out), n)
+    return out
+
+
 def run(ped: Pedigree, cols, lk, flags=None, method=ES, mrate=1e-7, lc=1.0, priors=None, burn=1000,
         rep=100000, rng=RNG_LIBC, seed=-1, v_offset=0):
     """Run the C restatement.  lk: [V][S][3] float64.  Returns dict(post, single, gt, status, post_full, single_full)."""
@@ -132,6 +145,16 @@ def run(ped: Pedigree, cols, lk, flags=None, method=ES, mrate=1e-7, lc=1.0, prio
     if rc != 0:
         raise RuntimeError(f"oracle error {rc}")
     return dict(post=post, single=single, gt=gt, status=status, post_full=pf, single_full=sf)
+
+
+def mcmc_sum_range():
+    """(min, max) Gibbs weight sum met by the chains of the last run(method=MCMC) call (test probe)."""
+    out = np.zeros(2)
+    lib().fso_mcmc_sum_range(_ptr(out))
+    return float(out[0]), float(out[1])
+
+
+FAST_SUM_LO, FAST_SUM_HI = 2.0 ** -963, 2.0 ** 963  # range of weight sums the generated Gibbs kernel handles itself
 
 
 def have_ref() -> bool:

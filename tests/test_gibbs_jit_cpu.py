@@ -69,6 +69,21 @@ static inline u8 call_genotype(double p0, double p1, double p2) {
 """
 
 
+def chain_stays_in_fast_range(ped, cols, lk, fl, burn, rep, seed, v_offset) -> bool:
+    """Runs the oracle's chain of ONE variant on the same Philox stream and reports whether every weight sum it met is
+    a positive normal number in [2^-963, 2^963) -- the range the generated kernel's straight-line code covers."""
+    O.run(ped, cols, lk, fl, method=O.MCMC, burn=burn, rep=rep, rng=O.RNG_PHILOX, seed=seed, v_offset=v_offset)
+    lo, hi = O.mcmc_sum_range()
+    if lo > hi:  # the sampler never ran (individual-only failure or LRC gate)
+        return True
+    return O.FAST_SUM_LO <= lo and hi < O.FAST_SUM_HI
+
+
+def lrc_gated(lk_row) -> bool:
+    """Every sample certain (largest likelihood == row sum): the default -LRC 1 gate skips the sampler."""
+    return bool(np.all(lk_row.max(-1) / lk_row.sum(-1) >= 1.0))
+
+
 def build_host_kernel(tmp_path, src: str):
     head = src[:src.index("typedef unsigned int u32;")]  # "// generated ..." comments and the TB / NCOL macros
     head = re.sub(r"#define TB \d+", "#define TB 1", head)  # one thread plays the block: cooperative loops cover everything
@@ -95,7 +110,7 @@ def test_generated_gibbs_code_reproduces_the_oracle(name, cols, V, tmp_path):
         src, _ = e.gibbs_kernel()
     lib = build_host_kernel(tmp_path, src)
     scratch = np.zeros(6 * ped.n * 1024 + 1024)  # block-private rows of 3 x TB doubles, TB <= 1024
-    checked = 0
+    checked = handed_back = 0
     for v in range(V):
         row_lk = np.ascontiguousarray(lk[v])
         flag = np.array([fl[v]], np.uint8)
@@ -103,8 +118,10 @@ def test_generated_gibbs_code_reproduces_the_oracle(name, cols, V, tmp_path):
         gt, status = np.zeros(S, np.uint8), np.full(1, 9, np.uint8)
         lib.famseq_gibbs(row_lk.ctypes.data, flag.ctypes.data, post.ctypes.data, single.ctypes.data, gt.ctypes.data, status.ctypes.data,
                          1, burn, rep, seed, v_offset + v, scratch.ctypes.data, 1)
-        if status[0] == 2:
-            continue  # a weight sum left the fast range: the table-driven kernel redoes such chains
+        if status[0] == 2:  # handed back to the table-driven kernel: legitimate only if a weight sum left the fast range
+            assert not chain_stays_in_fast_range(ped, cols, lk[v:v + 1], fl[v:v + 1], burn, rep, seed, v_offset + v), f"{name} variant {v}"
+            handed_back += 1
+            continue
         assert status[0] == want["status"][v], f"{name} variant {v}"
         if status[0]:
             continue
@@ -113,3 +130,40 @@ def test_generated_gibbs_code_reproduces_the_oracle(name, cols, V, tmp_path):
         assert np.array_equal(gt, want["gt"][v].astype(np.uint8))
         checked += 1
     assert checked >= V // 2
+
+
+def test_status_2_is_raised_exactly_when_a_weight_sum_leaves_the_fast_range(tmp_path):
+    """Likelihoods over a wide exponent range: some chains meet weight sums that are zero, subnormal or tiny.  The
+    generated code must flag exactly those (status 2, redone by the table-driven kernel) and agree with the oracle on
+    every other chain."""
+    ped = synth.half_sibs()
+    cols = ped.sequenced_cols()
+    S, V, burn, rep, seed, v_offset = len(cols), 60, 5, 40, 99, 7
+    rng = np.random.default_rng(3)
+    lk = rng.random((V, S, 3)) * np.exp2(rng.integers(-330, 1, (V, S, 3)).astype(np.float64))
+    lk[rng.random((V, S, 3)) < 0.05] = 0.0
+    fl = (rng.integers(0, 4, V)).astype(np.uint8)
+    want = O.run(ped, cols, lk, fl, method=O.MCMC, burn=burn, rep=rep, rng=O.RNG_PHILOX, seed=seed, v_offset=v_offset)
+    with fs.Engine(ped.ids, ped.mids, ped.fids, ped.genders, cols, device=-1) as e:
+        src, _ = e.gibbs_kernel()
+    lib = build_host_kernel(tmp_path, src)
+    scratch = np.zeros(6 * ped.n * 1024 + 1024)
+    flagged = clean = 0
+    for v in range(V):
+        row_lk, flag = np.ascontiguousarray(lk[v]), np.array([fl[v]], np.uint8)
+        post, single = np.zeros((S, 3)), np.zeros((S, 3))
+        gt, status = np.zeros(S, np.uint8), np.full(1, 9, np.uint8)
+        lib.famseq_gibbs(row_lk.ctypes.data, flag.ctypes.data, post.ctypes.data, single.ctypes.data, gt.ctypes.data, status.ctypes.data,
+                         1, burn, rep, seed, v_offset + v, scratch.ctypes.data, 1)
+        gated = want["status"][v] == 1 and not np.any(want["single"][v])  # failed before the sampler started
+        in_range = chain_stays_in_fast_range(ped, cols, lk[v:v + 1], fl[v:v + 1], burn, rep, seed, v_offset + v)
+        if status[0] == 2:
+            assert not in_range, f"variant {v} was handed back although its sums stay in the fast range"
+            flagged += 1
+            continue
+        assert gated or in_range or lrc_gated(lk[v]), f"variant {v} left the fast range without being handed back"
+        assert status[0] == want["status"][v], f"variant {v}"
+        if status[0] == 0:
+            assert np.allclose(post, want["post"][v], rtol=1e-9, atol=0), f"variant {v}"
+            clean += 1
+    assert flagged > 0 and clean > 0, (flagged, clean)

@@ -180,3 +180,34 @@ def test_generated_kernels_can_be_cached_on_disk(tmp_path, monkeypatch):
     assert sizes[0] == sizes[1] > 0 and "cubin loaded from" in logs[1] and "cubin loaded from" not in logs[0]
     assert len([f for f in os.listdir(tmp_path) if f.endswith(".cubin")]) == 1
     assert times[1] < times[0]
+
+
+def test_pl_decode_table_is_libm_pow_for_all_65536_values():
+    """fs_run_pl decodes uint16 PLs through a table built on the host with libm: lut[pl] == pow(10, -pl/10), the
+    expression of the reference's VCF driver (file.cpp:588-590), for every one of the 65 536 values -- checked against
+    the oracle's restatement (C, libm) and against Python's math.pow (libm as well; numpy's own power() differs in the
+    last bit for ~0.2 % of the values, which is why the table is not built with it)."""
+    import math
+
+    with host_engine(synth.trio()) as e:
+        lut = e.pl_table()
+    assert lut.shape == (65536,) and np.array_equal(lut, O.pl_table())
+    assert np.array_equal(lut, np.array([math.pow(10.0, -abs(float(k)) / 10.0) for k in range(65536)]))
+    assert lut[0] == 1.0 and lut[10] == 0.1 and lut[3236] > 0 and lut[3237] == 0.0 and not lut[3237:].any()
+    assert np.array_equal(synth.pl_to_likelihood(np.arange(70000)), np.concatenate([lut, np.zeros(70000 - 65536)]))
+
+
+def test_compact_entry_has_no_cpu_fallback_either():
+    with host_engine(synth.trio()) as e:
+        with pytest.raises(fs.FamSeqError) as ei:
+            e.run_pl(fs.ES, np.zeros((4, 3, 3), np.uint16))
+        assert ei.value.code == -6 and "no CPU fallback" in str(ei.value)
+        assert e.info()["n_devices"] == 0 and e.info()["mcmc_fixups"] == 0
+
+
+def test_multi_device_argument_checks():
+    ped = synth.trio()
+    for devices in ([], [0, 0], [1, 2, 1]):
+        with pytest.raises(fs.FamSeqError) as ei:
+            fs.Engine(ped.ids, ped.mids, ped.fids, ped.genders, ped.sequenced_cols(), device=devices)
+        assert ei.value.code == -1

@@ -14,7 +14,7 @@ import torch.multiprocessing as mp
 from famseq_b200 import sharding, synth
 from oracle import oracle as O
 
-V = 1500
+V = 1501  # odd on purpose: the two ranks own slices of different sizes
 
 
 def _free_port():
@@ -61,7 +61,7 @@ def test_two_ranks_reproduce_the_single_process_result(tmp_path):
     lk, fl = synth.synth_likelihoods(ped, V, seed=11, x_fraction=0.2)
     want = O.run(ped, ped.sequenced_cols(), lk, fl, method=O.ES)["post"]
     assert np.array_equal(np.load(out + ".es.npy"), want)  # gathered in site order, identical bytes
-    # the Gibbs stream is keyed by the global site index: rank 1's first sites equal sites 750.. of a single run
+    # the Gibbs stream is keyed by the global site index: rank 1's first sites equal sites 751.. of a single run
     lo1, _ = sharding.shard_range(V, 1, 2)
     single = O.run(ped, ped.sequenced_cols(), lk[lo1:lo1 + 40], fl[lo1:lo1 + 40], method=O.MCMC, burn=10, rep=100,
                    rng=O.RNG_PHILOX, seed=5, v_offset=lo1)["post"]

@@ -53,3 +53,33 @@ def assert_parity(got, want, tol=REL_TOL, what=""):
     assert e1 <= tol, f"{what}: single posterior rel err {e1:.3e} > {tol}"
     assert e2 <= tol, f"{what}: pedigree posterior rel err {e2:.3e} > {tol}"
     return e1, e2
+
+
+# ---- statistical MCMC parity ------------------------------------------------------
+MCMC16_DIR = os.path.join(GOLDEN_DIR, "mcmc16")
+MCMC_Z = 4.0
+
+
+def mcmc16_cases():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(MCMC16_DIR, "*.npz")))
+
+
+def load_mcmc16(name):
+    return dict(np.load(os.path.join(MCMC16_DIR, name + ".npz")))
+
+
+def mcmc_z_scores(ours_runs, ref_mean, ref_se, ok):
+    """Per-entry z of SURVEY 8(c): |mean_ours - mean_ref| / sqrt(se_ours^2 + se_ref^2), standard errors from the R
+    independent seeds of each side.  Entries whose spread is zero on both sides (the chains never leave one state:
+    the posterior is a deterministic function of the likelihoods there) must agree to 1e-9 relative instead and get
+    z = 0 when they do, inf when they do not."""
+    ours_runs = np.asarray(ours_runs)[:, ok]
+    R = ours_runs.shape[0]
+    mean = ours_runs.mean(0)
+    se = ours_runs.std(0, ddof=1) / np.sqrt(R)
+    rm, rs = ref_mean[ok], ref_se[ok]
+    den = np.sqrt(se * se + rs * rs)
+    diff = np.abs(mean - rm)
+    exact = den == 0
+    z = np.where(exact, np.where(diff <= 1e-9 * np.abs(rm), 0.0, np.inf), diff / np.where(exact, 1.0, den))
+    return z, mean, se
