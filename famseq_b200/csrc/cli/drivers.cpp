@@ -1,14 +1,20 @@
 // drivers.cpp -- see drivers.hpp.
 //
 // The reference handles one record at a time (parse, set_LK, calPostProb*, print).  Here the text side
-// keeps the reference's record rules and output bytes, but records are collected into batches of up to
-// kBatch variants, sent through one fs_run() call (H2D / kernel / D2H pipelined inside the engine) and
-// then printed in input order.  Likelihood decoding (pow, exp) and Phred encoding (log10) stay on the
-// host with libm so that the engine sees bit-identical inputs ("hard parts").
+// keeps the reference's record rules and output bytes, but records travel in blocks of up to kBatch lines
+// through a three-stage pipeline whose stages overlap:
+//     parse(k+1)  ||  engine(k)  ||  format(k-1)  ||  file write
+// parse and format are spread over the host threads, the engine stage is one fs_run_pl() / fs_run() call on
+// pinned buffers (H2D / kernel / D2H pipelined inside the engine), output order is input order.
+// Integer PL fields go to the engine as they stand (uint16, decoded on the device through the engine's
+// host-libm table: the host never calls pow for them); anything else (GL, decimals, the LK modes) is decoded on
+// the host with libm and takes the FP64 entry.  Phred encoding (log10) stays on the host so that the text is
+// byte-identical to the reference's.
 #include "drivers.hpp"
 #include "format_g.hpp"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -19,6 +25,10 @@
 #include <limits>
 #include <sstream>
 #include <string_view>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <condition_variable>
 #include <deque>
 #include <mutex>
@@ -34,7 +44,8 @@ bool g_engine_failed = false;
 namespace {
 
 using sv = std::string_view;
-constexpr size_t kBatch = 1u << 18;
+constexpr size_t kBatch = 1u << 17; // record lines per pipeline block
+constexpr int kSlots = 4;             // blocks in flight (parse / engine / format + one of slack)
 
 double now() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -96,26 +107,76 @@ bool read_file(const std::string &path, std::string &data) {
     return ok;
 }
 
+// The whole input as one string_view: regular files are mapped (no copy; the page faults are taken by the parsing
+// threads), anything else (pipes, process substitutions) is read to the end into memory.
+class InputFile {
+  public:
+    ~InputFile() {
+        if (map_) munmap(map_, size_);
+    }
+    bool open(const std::string &path) {
+        const int fd = ::open(path.c_str(), O_RDONLY);
+        if (fd < 0) return false;
+        struct stat st;
+        if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 0) {
+            void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (m != MAP_FAILED) {
+                map_ = m;
+                size_ = (size_t)st.st_size;
+                madvise(m, size_, MADV_WILLNEED);
+                ::close(fd);
+                return true;
+            }
+        }
+        ::close(fd);
+        return read_file(path, data_);
+    }
+    sv view() const { return map_ ? sv(static_cast<const char *>(map_), size_) : sv(data_); }
+
+  private:
+    void *map_ = nullptr;
+    size_t size_ = 0;
+    std::string data_;
+};
+
 // getline()-style cursor over an in-memory file.  Mirrors `while(!fin.eof()) getline(fin, line)`: after the last
 // newline one more, empty, line is delivered.
 struct Lines {
-    const std::string &data;
+    sv data;
     size_t pos = 0;
     bool done = false;
-    explicit Lines(const std::string &d) : data(d) {}
+    explicit Lines(sv d) : data(d) {}
     bool next(sv &line) {
         if (done) return false;
-        const size_t nl = data.find('\n', pos);
-        if (nl == std::string::npos) {
-            line = sv(data).substr(pos);
+        const void *hit = pos < data.size() ? std::memchr(data.data() + pos, '\n', data.size() - pos) : nullptr;
+        if (!hit) {
+            line = data.substr(pos);
             done = true;
         } else {
-            line = sv(data).substr(pos, nl - pos);
+            const size_t nl = (size_t)(static_cast<const char *>(hit) - data.data());
+            line = data.substr(pos, nl - pos);
             pos = nl + 1;
         }
         return true;
     }
 };
+
+// A PL-like field as the engine's compact input wants it: the whole token is an optionally signed run of digits.
+// |value| is returned clamped to 65535 (every PL >= 3237 decodes to exactly 0.0, so the clamp is exact).  False for
+// anything else (decimals, exponents, blanks, empty): the caller then takes atof() and the FP64 path.
+inline bool integer_field(sv s, uint16_t &out) {
+    size_t i = 0;
+    if (i < s.size() && (s[i] == '-' || s[i] == '+')) i++;
+    if (i == s.size()) return false;
+    unsigned v = 0;
+    for (; i < s.size(); i++) {
+        const unsigned d = (unsigned)(s[i] - '0');
+        if (d > 9) return false;
+        v = std::min(v * 10 + d, 1000000u);
+    }
+    out = (uint16_t)std::min(v, 65535u);
+    return true;
+}
 
 // ostream's default formatting of a double is printf's %g with 6 significant digits (format_g.hpp: same bytes, faster).
 void put_number(std::string &out, double v) { famseq::append_g(out, v); }
@@ -201,15 +262,12 @@ ColumnMap map_columns(const std::vector<sv> &names, size_t first, const PedRows 
     return m;
 }
 
-// The engine(s) of a run: one fs_engine per CUDA device.  With several devices every batch is cut into contiguous
-// slices, one per device, computed concurrently (variants are independent; the Gibbs sampler's streams are keyed by the
-// global variant index, so the output does not depend on the number of devices).
+// The engine of a run: ONE fs_engine, over one GPU or (fs_create_multi) over several -- every batch is then cut into
+// contiguous slices, one per device, inside the engine (variants are independent; the Gibbs sampler's streams are
+// keyed by the global variant index, so the output does not depend on the number of devices).
 struct Engine {
-    std::vector<fs_engine *> h;
-    std::vector<int> device;
-    ~Engine() {
-        for (fs_engine *e : h) fs_destroy(e);
-    }
+    fs_engine *h = nullptr;
+    ~Engine() { fs_destroy(h); }
     static std::vector<int> resolve(const std::vector<int> &wanted, int fallback) {
         if (wanted.empty()) return {fallback};
         if (wanted[0] >= 0) return wanted;
@@ -222,73 +280,115 @@ struct Engine {
             fa(ped.father_id.begin(), ped.father_id.end()), ge(ped.gender.begin(), ped.gender.end());
         fs_pedigree fp{(int32_t)id.size(), id.data(), mo.data(), fa.data(), ge.data(), (int32_t)cm.engine_cols.size(),
                        cm.engine_cols.data()};
-        device = devices;
-        h.assign(devices.size(), nullptr);
-        std::vector<std::string> err(devices.size());
-        std::vector<std::thread> pool; // CUDA contexts are created side by side
-        for (size_t k = 0; k < devices.size(); k++)
-            pool.emplace_back([&, k] {
-                if (fs_create(&fp, &prm, devices[k], &h[k]) != FS_OK) err[k] = fs_last_error();
-            });
-        for (auto &t : pool) t.join();
-        for (const std::string &e : err)
-            if (!e.empty()) {
-                std::cout << e << std::endl;
-                g_engine_failed = true;
-                return false;
-            }
+        if (fs_create_multi(&fp, &prm, devices.data(), (int)devices.size(), &h) != FS_OK) {
+            std::cout << fs_last_error() << std::endl;
+            g_engine_failed = true;
+            return false;
+        }
         return true;
     }
 };
 
-// One batch of records waiting for the engine.
-struct Pending {
-    std::vector<double> lk;
-    std::vector<uint8_t> flags;
-    std::vector<double> post, single;
-    std::vector<uint8_t> gt, status;
-    size_t count() const { return flags.size(); }
-    void clear() {
-        lk.clear();
-        flags.clear();
+// Pinned host buffers of one pipeline slot (fs_alloc_pinned: the engine's copies then run at full PCIe speed and
+// asynchronously).  Allocated by the engine stage, i.e. after the CUDA context exists.
+struct HostBuffers {
+    size_t cap = 0; // variants
+    uint16_t *pl = nullptr;
+    double *lk = nullptr, *post = nullptr, *single = nullptr;
+    uint8_t *flags = nullptr, *gt = nullptr, *status = nullptr;
+    ~HostBuffers() { release(); }
+    void release() {
+        fs_free_pinned(pl);
+        fs_free_pinned(lk);
+        fs_free_pinned(post);
+        fs_free_pinned(single);
+        fs_free_pinned(flags);
+        fs_free_pinned(gt);
+        fs_free_pinned(status);
+        pl = nullptr, lk = post = single = nullptr, flags = gt = status = nullptr, cap = 0;
     }
-    bool run(Engine &e, int method, int S, int burn, int rep, unsigned long long seed, long long v_offset) {
-        const size_t V = count();
-        post.resize(V * S * 3);
-        single.resize(V * S * 3);
-        gt.resize(V * S);
-        status.resize(V);
-        const double t0 = now();
-        const size_t G = e.h.size();
-        std::vector<std::string> err(G);
-        std::vector<double> kernel_ms(G, 0.0);
-        auto slice = [&](size_t g) {
-            const size_t lo = V * g / G, hi = V * (g + 1) / G;
-            if (hi == lo) return;
-            const int rc = fs_run(e.h[g], method, (int64_t)(hi - lo), lk.data() + lo * S * 3, flags.data() + lo, burn, rep, seed,
-                                  v_offset + (long long)lo, post.data() + lo * S * 3, single.data() + lo * S * 3, gt.data() + lo * S,
-                                  status.data() + lo);
-            if (rc != FS_OK) err[g] = fs_last_error();
-            kernel_ms[g] = fs_last_kernel_ms(e.h[g]);
-        };
-        if (G == 1) {
-            slice(0);
-        } else {
-            std::vector<std::thread> pool;
-            for (size_t g = 0; g < G; g++) pool.emplace_back(slice, g);
-            for (auto &t : pool) t.join();
+    bool reserve(size_t variants, size_t S, bool want_lk) {
+        if (variants > cap) {
+            release();
+            cap = std::max(variants, kBatch);
+            const size_t n3 = std::max<size_t>(cap * S * 3, 1);
+            pl = static_cast<uint16_t *>(fs_alloc_pinned(n3 * sizeof(uint16_t)));
+            post = static_cast<double *>(fs_alloc_pinned(n3 * sizeof(double)));
+            single = static_cast<double *>(fs_alloc_pinned(n3 * sizeof(double)));
+            flags = static_cast<uint8_t *>(fs_alloc_pinned(cap));
+            gt = static_cast<uint8_t *>(fs_alloc_pinned(std::max<size_t>(cap * S, 1)));
+            status = static_cast<uint8_t *>(fs_alloc_pinned(cap));
+            if (!pl || !post || !single || !flags || !gt || !status) return false;
         }
-        g_stats.engine_s += now() - t0;
-        g_stats.kernel_ms += *std::max_element(kernel_ms.begin(), kernel_ms.end());
-        g_stats.batches++;
-        for (const std::string &m : err)
-            if (!m.empty()) {
-                std::cout << m << std::endl;
-                g_engine_failed = true;
-                return false;
-            }
+        if (want_lk && !lk) lk = static_cast<double *>(fs_alloc_pinned(std::max<size_t>(cap * S * 3, 1) * sizeof(double)));
+        return !want_lk || lk;
+    }
+};
+
+// What a host thread parsed from / formats for its contiguous range of a block.
+struct Part {
+    std::vector<sv> lines;        // records that produce output, in input order
+    std::vector<uint8_t> echo;    // per line: 1 = echoed as it stands (VCF skip rules), 0 = computed
+    std::vector<uint16_t> pl;     // compact likelihoods [count][S][3] (while `compact`)
+    std::vector<double> lk;       // FP64 likelihoods   [count][S][3] (once a field was not an integer)
+    std::vector<uint8_t> flags;   // [count]
+    bool compact = true;
+    std::string out, warn;
+    long long failed = 0;
+    size_t first = 0; // index of this part's first computed variant inside the block
+    size_t count() const { return flags.size(); }
+    void reset() {
+        lines.clear(), echo.clear(), pl.clear(), lk.clear(), flags.clear();
+        compact = true;
+    }
+    // a non-integer field was met: continue in FP64 (what is already there decodes through the same table the device uses)
+    void widen(const double *table) {
+        if (!compact) return;
+        lk.resize(pl.size());
+        for (size_t k = 0; k < pl.size(); k++) lk[k] = table[pl[k]];
+        pl.clear();
+        compact = false;
+    }
+};
+
+struct Block {
+    std::vector<sv> lines;
+    std::vector<Part> parts;
+    size_t total = 0;
+    long long v_offset = 0;
+    bool compact = true;
+    HostBuffers buf;
+};
+
+// Bounded FIFO between two pipeline stages; close() wakes everybody up (end of input or failure).
+template <class T> class Channel {
+  public:
+    bool push(T v) {
+        std::unique_lock<std::mutex> lk(m_);
+        if (closed_) return false;
+        q_.push_back(v);
+        cv_.notify_all();
         return true;
     }
+    bool pop(T &v) {
+        std::unique_lock<std::mutex> lk(m_);
+        cv_.wait(lk, [this] { return closed_ || !q_.empty(); });
+        if (q_.empty()) return false;
+        v = q_.front();
+        q_.pop_front();
+        return true;
+    }
+    void close() {
+        std::lock_guard<std::mutex> lk(m_);
+        closed_ = true;
+        cv_.notify_all();
+    }
+
+  private:
+    std::mutex m_;
+    std::condition_variable cv_;
+    std::deque<T> q_;
+    bool closed_ = false;
 };
 
 // Number of host threads for parsing / formatting: FAMSEQ_THREADS or the hardware concurrency (at most 64).
@@ -369,13 +469,178 @@ class EngineStart {
     std::thread th_;
 };
 
+// The record pipeline shared by the two drivers.
+//   accept(line): 0 = the input ends here, 1 = a record, 2 = skip the line
+//   parse(part, lines, n, compact): fills `part` from n record lines; with compact = true it returns false as soon as a
+//                                   likelihood field is not an integer (the range is then parsed again in FP64)
+//   format(part, results): writes part.out / part.warn / part.failed from the engine's results of the part's block
+struct BlockResults {
+    const double *post, *single;
+    const uint8_t *gt, *status;
+};
+struct PipelineSetup {
+    Engine *engine;
+    EngineStart *start;
+    int S, method, burn, rep;
+    unsigned long long seed;
+    AsyncWriter *writer;
+};
+
+template <class Accept, class Parse, class Format>
+bool run_pipeline(Lines &in, const PipelineSetup &ps, Accept accept, Parse parse, Format format) {
+    const int n_threads = host_threads();
+    const size_t S = (size_t)ps.S;
+    std::vector<Block> blocks((size_t)kSlots);
+    Channel<Block *> free_q, engine_q, format_q;
+    for (Block &b : blocks) {
+        b.parts.resize((size_t)n_threads);
+        free_q.push(&b);
+    }
+    std::atomic<bool> ok{true};
+    auto abort_all = [&]() {
+        ok = false;
+        free_q.close();
+        engine_q.close();
+        format_q.close();
+    };
+
+    // ---- stage A: cut the input into blocks and parse them ---------------------------------------------------
+    std::thread stage_a([&] {
+        long long v_offset = 0;
+        bool eof = false;
+        Block *b = nullptr;
+        while (!eof && free_q.pop(b)) {
+            const double t0 = now();
+            b->lines.clear();
+            sv line;
+            while (b->lines.size() < kBatch) {
+                if (!in.next(line)) {
+                    eof = true;
+                    break;
+                }
+                const int what = accept(line);
+                if (what == 0) {
+                    eof = true;
+                    break;
+                }
+                if (what == 1) b->lines.push_back(line);
+            }
+            if (b->lines.empty()) break;
+            g_stats.records += (long long)b->lines.size();
+            run_parallel(n_threads, [&](int t) {
+                const size_t lo = b->lines.size() * (size_t)t / n_threads, hi = b->lines.size() * (size_t)(t + 1) / n_threads;
+                Part &P = b->parts[t];
+                P.reset();
+                if (!parse(P, b->lines.data() + lo, hi - lo, true)) {
+                    P.reset();
+                    P.compact = false;
+                    parse(P, b->lines.data() + lo, hi - lo, false);
+                }
+            });
+            b->total = 0;
+            b->compact = true;
+            for (Part &P : b->parts) {
+                P.first = b->total;
+                b->total += P.count();
+                b->compact = b->compact && (P.compact || P.count() == 0);
+            }
+            b->v_offset = v_offset;
+            v_offset += (long long)b->total;
+            g_stats.parse_s += now() - t0;
+            if (!engine_q.push(b)) break;
+        }
+        engine_q.close();
+    });
+
+    // ---- stage B: one engine call per block on pinned buffers ----------------------------------------------------
+    std::thread stage_b([&] {
+        std::vector<double> table;
+        Block *b = nullptr;
+        while (engine_q.pop(b)) {
+            if (b->total) {
+                double t0 = now();
+                const bool ready = ps.start->wait();
+                g_stats.start_wait_s += now() - t0;
+                if (!ready) break;
+                t0 = now();
+                if (!b->buf.reserve(b->total, S, !b->compact)) {
+                    std::cout << "Cannot allocate pinned host memory for a block of " << b->total << " variants" << std::endl;
+                    g_engine_failed = true;
+                    break;
+                }
+                if (!b->compact && table.empty()) {
+                    table.resize(FS_PL_TABLE_SIZE);
+                    fs_get_pl_table(ps.engine->h, table.data());
+                }
+                for (Part &P : b->parts) {
+                    if (!P.count()) continue;
+                    std::memcpy(b->buf.flags + P.first, P.flags.data(), P.count());
+                    const size_t n3 = P.count() * S * 3, off = P.first * S * 3;
+                    if (b->compact)
+                        std::memcpy(b->buf.pl + off, P.pl.data(), n3 * sizeof(uint16_t));
+                    else if (P.compact)
+                        for (size_t k = 0; k < n3; k++) b->buf.lk[off + k] = table[P.pl[k]];
+                    else
+                        std::memcpy(b->buf.lk + off, P.lk.data(), n3 * sizeof(double));
+                }
+                const int rc = b->compact ? fs_run_pl(ps.engine->h, ps.method, (int64_t)b->total, b->buf.pl, b->buf.flags, ps.burn, ps.rep, ps.seed,
+                                                      b->v_offset, b->buf.post, b->buf.single, b->buf.gt, b->buf.status)
+                                          : fs_run(ps.engine->h, ps.method, (int64_t)b->total, b->buf.lk, b->buf.flags, ps.burn, ps.rep, ps.seed,
+                                                   b->v_offset, b->buf.post, b->buf.single, b->buf.gt, b->buf.status);
+                g_stats.engine_s += now() - t0;
+                g_stats.kernel_ms += fs_last_kernel_ms(ps.engine->h);
+                g_stats.batches++;
+                if (b->compact) g_stats.compact_batches++;
+                if (rc != FS_OK) {
+                    std::cout << fs_last_error() << std::endl;
+                    g_engine_failed = true;
+                    break;
+                }
+            }
+            if (!format_q.push(b)) break;
+            b = nullptr;
+        }
+        if (g_engine_failed || !ok) abort_all();
+        format_q.close();
+    });
+
+    // ---- stage C (this thread): format and hand to the writer, in order ------------------------------------------
+    {
+        Block *b = nullptr;
+        while (format_q.pop(b)) {
+            const double t0 = now();
+            const BlockResults res{b->buf.post, b->buf.single, b->buf.gt, b->buf.status};
+            run_parallel(n_threads, [&](int t) { format(b->parts[t], res); });
+            for (Part &P : b->parts) {
+                ps.writer->push(std::move(P.out));
+                P.out.clear();
+                if (!P.warn.empty()) std::cout << P.warn << std::flush;
+                g_stats.failed += P.failed;
+            }
+            g_stats.computed += (long long)b->total;
+            g_stats.write_s += now() - t0;
+            if (!free_q.push(b)) break;
+        }
+    }
+    if (g_engine_failed) abort_all();
+    free_q.close();
+    stage_a.join();
+    stage_b.join();
+    // an input without records still reports a pedigree the engine rejects
+    const double t0 = now();
+    const bool ready = ps.start->wait();
+    g_stats.start_wait_s += now() - t0;
+    return ok && ready && !g_engine_failed;
+}
+
+
 void emit_stats() {
     if (!std::getenv("FAMSEQ_STATS")) return;
     std::fprintf(stderr,
-                 "{\"records\": %lld, \"computed\": %lld, \"failed\": %lld, \"batches\": %lld, \"parse_s\": %.4f, "
+                 "{\"records\": %lld, \"computed\": %lld, \"failed\": %lld, \"batches\": %lld, \"compact_batches\": %lld, \"parse_s\": %.4f, "
                  "\"engine_s\": %.4f, \"kernel_ms\": %.3f, \"write_s\": %.4f, \"read_s\": %.4f, \"start_wait_s\": %.4f, "
                  "\"drain_s\": %.4f, \"total_s\": %.4f}\n",
-                 g_stats.records, g_stats.computed, g_stats.failed, g_stats.batches, g_stats.parse_s, g_stats.engine_s,
+                 g_stats.records, g_stats.computed, g_stats.failed, g_stats.batches, g_stats.compact_batches, g_stats.parse_s, g_stats.engine_s,
                  g_stats.kernel_ms, g_stats.write_s, g_stats.read_s, g_stats.start_wait_s, g_stats.drain_s, g_stats.total_s);
 }
 
@@ -428,11 +693,6 @@ bool check_family(const PedRows &ped) {
 // --------------------------------------------------------------------------------------------------------
 namespace {
 
-struct VcfItem {
-    enum Kind : uint8_t { Echo, Compute } kind;
-    sv line;
-};
-
 int chrom_number(sv chrom) { // file.cpp:460-466
     if (chrom.substr(0, 3) == "chr") return to_int(chrom.substr(3));
     return to_int(chrom);
@@ -460,12 +720,13 @@ bool run_vcf(const VcfOptions &opt, const PedRows &ped) {
         std::thread &t;
         ~Joiner() { if (t.joinable()) t.join(); }
     } warm_joiner{warm};
-    std::string data;
+    InputFile input;
     const double t_read = now();
-    if (!read_file(vcf_name, data)) {
+    if (!input.open(vcf_name)) {
         std::cout << "Cannot open " << vcf_name << std::endl;
         return false;
     }
+    const sv data = input.view();
     g_stats.read_s = now() - t_read;
     FILE *fout = std::fopen(opt.output.c_str(), "wb");
     if (!fout) {
@@ -569,40 +830,16 @@ bool run_vcf(const VcfOptions &opt, const PedRows &ped) {
     }
 
     Engine eng;
-    EngineStart eng_start(eng, ped, cm, prm, Engine::resolve(opt.devices, opt.device)); // joined before the first batch (or at the end of an empty input)
-    auto engine_ready = [&]() {
-        const double t0 = now();
-        const bool ready = eng_start.wait();
-        g_stats.start_wait_s += now() - t0;
-        return ready;
-    };
+    EngineStart eng_start(eng, ped, cm, prm, Engine::resolve(opt.devices, opt.device)); // joined before the first engine call (or at the end of an empty input)
     int burn = opt.num_burn_in, rep = opt.num_rep; // file.cpp:644-656
     if (burn < 0) burn = 1000 * real_num_ind;
     if (rep < 0) rep = 20000 * real_num_ind;
 
     // ---- pass 2: records ---------------------------------------------------------------------------------------
-    // Blocks of up to kBatch record lines.  Parsing (tokenise, skip rules, PL -> likelihood) and formatting
-    // (Phred encode, "%g") are spread over host threads, each owning a contiguous range of the block; the engine
-    // call in between sees one batch.  Output order is the input order.
-    struct Part {
-        std::vector<VcfItem> items;
-        std::vector<double> lk;
-        std::vector<uint8_t> flags;
-        std::string out, warn;
-        long long failed = 0;
-        size_t first = 0; // index of this part's first computed variant inside the batch
-    };
-    const int n_threads = host_threads();
-    std::vector<Part> parts((size_t)n_threads);
-    Pending batch;
-    long long v_offset = 0;
-    bool ok = true;
-
-    auto parse_range = [&](Part &P, const sv *lines, size_t n) {
+    // Parsing (tokenise, skip rules, PL fields) and formatting (Phred encode, "%g") are spread over host threads, each
+    // owning a contiguous range of a block; see run_pipeline.
+    auto parse_range = [&](Part &P, const sv *lines, size_t n, bool compact) -> bool {
         std::vector<sv> col, fmt, sub, pl;
-        P.items.clear();
-        P.lk.clear();
-        P.flags.clear();
         for (size_t li = 0; li < n; li++) {
             const sv line = lines[li];
             split(line, '\t', col);
@@ -615,8 +852,12 @@ bool run_vcf(const VcfOptions &opt, const PedRows &ped) {
                 if (pos == 0) continue;
                 if (!std::binary_search(location[chr - 1].begin(), location[chr - 1].end(), pos)) continue;
             }
+            auto echo = [&]() {
+                P.lines.push_back(line);
+                P.echo.push_back(1);
+            };
             auto skip = [&]() {
-                if (all_line) P.items.push_back({VcfItem::Echo, line});
+                if (all_line) echo();
             };
             if (ref == "." || ref == "-") { skip(); continue; }
             if (ref.size() != 1 || alt.size() != 1) { skip(); continue; }
@@ -635,39 +876,60 @@ bool run_vcf(const VcfOptions &opt, const PedRows &ped) {
             for (size_t i = 0; i < fmt.size(); i++)
                 if (fmt[i] == "PL" || fmt[i] == "GL") ind_pl = (int)i; // the last one wins; GL is decoded like PL
             if (ind_pl < 0) { // no likelihoods: the record is echoed whatever -a says (file.cpp:541-555)
-                P.items.push_back({VcfItem::Echo, line});
+                echo();
                 continue;
             }
-            // likelihoods: pow(10, -|PL|/10); missing or malformed sample fields keep (1,1,1) (file.cpp:565-593, :794-831)
-            const size_t base = P.lk.size();
-            P.lk.resize(base + (size_t)S * 3, 1.0);
+            // likelihoods: pow(10, -|PL|/10); missing or malformed sample fields keep (1,1,1) (file.cpp:565-593, :794-831).
+            // Compact: the integer itself (0 = likelihood 1), decoded on the device through the engine's libm-built table.
+            size_t base;
+            if (compact) {
+                base = P.pl.size();
+                P.pl.resize(base + (size_t)S * 3, 0);
+            } else {
+                base = P.lk.size();
+                P.lk.resize(base + (size_t)S * 3, 1.0);
+            }
             for (size_t k = 0; k < cm.matched.size(); k++) {
                 const sv field = col[9 + cm.matched[k]];
-                double *dst = &P.lk[base + (size_t)cm.unique[k] * 3];
+                const size_t at = base + (size_t)cm.unique[k] * 3;
                 if (n_miss > 0 && field.size() < 5) {
-                    dst[0] = dst[1] = dst[2] = 1.0;
+                    for (int j = 0; j < 3; j++) {
+                        if (compact)
+                            P.pl[at + j] = 0;
+                        else
+                            P.lk[at + j] = 1.0;
+                    }
                     continue;
                 }
                 split(field, ':', sub);
                 if (sub.size() != fmt.size()) continue;
                 split(sub[ind_pl], ',', pl);
-                for (size_t j = 0; j < 3 && j < pl.size(); j++) dst[j] = std::pow(10.0, -std::fabs(to_double(pl[j])) / 10.0);
+                for (size_t j = 0; j < 3 && j < pl.size(); j++) {
+                    if (compact) {
+                        if (!integer_field(pl[j], P.pl[at + j])) return false; // GL, decimals, ...: this range goes the FP64 way
+                    } else {
+                        P.lk[at + j] = std::pow(10.0, -std::fabs(to_double(pl[j])) / 10.0);
+                    }
+                }
             }
             P.flags.push_back((uint8_t)((known ? FS_FLAG_KNOWN : 0) | (chrx ? FS_FLAG_CHRX : 0)));
-            P.items.push_back({VcfItem::Compute, line});
+            P.lines.push_back(line);
+            P.echo.push_back(0);
         }
+        return true;
     };
 
-    auto format_range = [&](Part &P) {
+    auto format_range = [&](Part &P, const BlockResults &R) {
         std::vector<sv> col, fmt;
         std::string &o = P.out;
         o.clear();
         P.warn.clear();
         P.failed = 0;
         size_t v = P.first;
-        for (const VcfItem &it : P.items) {
-            split(it.line, '\t', col);
-            if (it.kind == VcfItem::Echo) { // first nine columns and the matched samples, each followed by a tab
+        for (size_t li = 0; li < P.lines.size(); li++) {
+            const sv line = P.lines[li];
+            split(line, '\t', col);
+            if (P.echo[li]) { // first nine columns and the matched samples, each followed by a tab
                 for (int i = 0; i < 9; i++) {
                     o.append(col[i]);
                     o += '\t';
@@ -686,10 +948,10 @@ bool run_vcf(const VcfOptions &opt, const PedRows &ped) {
             }
             o.append(col[8]);
             o += ":GPP:FPP:FGT\t";
-            const bool failed = batch.status[v] != 0;
+            const bool failed = R.status[v] != 0;
             if (failed) { // file.cpp:607-619
                 P.warn += "Warning: this variant hasn't been calculated: \n";
-                P.warn.append(it.line);
+                P.warn.append(line);
                 P.warn += '\n';
                 P.failed++;
             }
@@ -709,7 +971,7 @@ bool run_vcf(const VcfOptions &opt, const PedRows &ped) {
                     o += ':';
                 }
                 const size_t off = (v * S + cm.unique[k]) * 3;
-                put_calls(o, &batch.single[off], &batch.post[off], batch.gt[v * S + cm.unique[k]]);
+                put_calls(o, &R.single[off], &R.post[off], R.gt[v * S + cm.unique[k]]);
             }
             o += '\n';
             v++;
@@ -720,55 +982,10 @@ bool run_vcf(const VcfOptions &opt, const PedRows &ped) {
     writer.push(std::move(out)); // header
     out.clear();
     Lines in(data);
-    std::vector<sv> block;
-    bool eof = false;
-    while (!eof && ok) {
-        double t0 = now();
-        block.clear();
-        sv line;
-        while (block.size() < kBatch) {
-            if (!in.next(line) || line.size() < 2) { // the reference stops at the first line shorter than two characters
-                eof = true;
-                break;
-            }
-            if (line[0] == '#') continue;
-            block.push_back(line);
-        }
-        if (block.empty()) break;
-        g_stats.records += (long long)block.size();
-        run_parallel(n_threads, [&](int t) {
-            const size_t lo = block.size() * (size_t)t / n_threads, hi = block.size() * (size_t)(t + 1) / n_threads;
-            parse_range(parts[t], block.data() + lo, hi - lo);
-        });
-        size_t total = 0;
-        for (Part &P : parts) {
-            P.first = total;
-            total += P.flags.size();
-        }
-        batch.lk.resize(total * S * 3);
-        batch.flags.resize(total);
-        for (Part &P : parts) {
-            if (P.flags.empty()) continue;
-            std::memcpy(&batch.lk[P.first * S * 3], P.lk.data(), P.lk.size() * sizeof(double));
-            std::memcpy(&batch.flags[P.first], P.flags.data(), P.flags.size());
-        }
-        g_stats.parse_s += now() - t0;
-        if (total && (!engine_ready() || !batch.run(eng, opt.method, S, burn, rep, opt.seed, v_offset))) {
-            ok = false;
-            break;
-        }
-        t0 = now();
-        run_parallel(n_threads, [&](int t) { format_range(parts[t]); });
-        for (Part &P : parts) {
-            writer.push(std::move(P.out));
-            if (!P.warn.empty()) std::cout << P.warn << std::flush;
-            g_stats.failed += P.failed;
-        }
-        v_offset += (long long)total;
-        g_stats.computed += (long long)total;
-        g_stats.write_s += now() - t0;
-    }
-    if (!engine_ready()) ok = false; // an input without records still reports a pedigree the engine rejects
+    // the reference stops at the first line shorter than two characters; header lines are not records
+    auto accept = [](sv line) { return line.size() < 2 ? 0 : (line[0] == '#' ? 2 : 1); };
+    const PipelineSetup setup{&eng, &eng_start, S, opt.method, burn, rep, opt.seed, &writer};
+    bool ok = run_pipeline(in, setup, accept, parse_range, format_range);
     {
         const double t0 = now();
         const bool written = writer.close();
@@ -797,11 +1014,12 @@ bool run_lk(const LkOptions &opt, const PedRows &ped) {
         std::thread &t;
         ~Joiner() { if (t.joinable()) t.join(); }
     } warm_joiner{warm};
-    std::string data;
-    if (!read_file(opt.lk_file, data)) {
+    InputFile input;
+    if (!input.open(opt.lk_file)) {
         std::cout << "Cannot open " << opt.lk_file << std::endl;
         return false;
     }
+    const sv data = input.view();
     FILE *fout = std::fopen(opt.output.c_str(), "wb");
     if (!fout) {
         std::cout << "Cannot open " << opt.output << std::endl;
@@ -833,54 +1051,48 @@ bool run_lk(const LkOptions &opt, const PedRows &ped) {
     const int S = (int)cm.engine_cols.size();
 
     Engine eng;
-    EngineStart eng_start(eng, ped, cm, prm, Engine::resolve(opt.devices, opt.device)); // joined before the first batch (or at the end of an empty input)
-    auto engine_ready = [&]() {
-        const double t0 = now();
-        const bool ready = eng_start.wait();
-        g_stats.start_wait_s += now() - t0;
-        return ready;
-    };
+    EngineStart eng_start(eng, ped, cm, prm, Engine::resolve(opt.devices, opt.device)); // joined before the first engine call (or at the end of an empty input)
 
-    // blocks of up to kBatch rows; decoding and formatting are spread over host threads (see run_vcf)
-    struct Part {
-        std::vector<sv> lines;
-        std::vector<double> lk;
-        std::string out, warn;
-        long long failed = 0;
-        size_t first = 0;
-    };
-    const int n_threads = host_threads();
-    std::vector<Part> parts((size_t)n_threads);
-    Pending batch;
-    long long v_offset = 0;
-    bool ok = true;
-
-    auto parse_range = [&](Part &P, const sv *rows, size_t n) {
+    // decoding and formatting are spread over host threads (see run_vcf / run_pipeline).  The LK driver calls the engine
+    // with Known = false, chrType = 0 (file.cpp:1751,1768,1785): flags stay 0.  Phred-scaled rows (-lkType PS) of
+    // non-negative integers go to the engine as they stand, like VCF PL fields; everything else is decoded here.
+    auto parse_range = [&](Part &P, const sv *rows, size_t n, bool compact) -> bool {
         std::vector<sv> col, pl;
-        P.lines.clear();
-        P.lk.clear();
+        if (compact && opt.lk_type != 4) return false;
         for (size_t li = 0; li < n; li++) {
             split(rows[li], '\t', col);
             if (col.size() < cm.ped_row.size()) continue; // malformed row: the reference would read out of bounds
-            const size_t base = P.lk.size();
-            P.lk.resize(base + (size_t)S * 3, 1.0);
+            size_t base;
+            if (compact) {
+                base = P.pl.size();
+                P.pl.resize(base + (size_t)S * 3, 0);
+            } else {
+                base = P.lk.size();
+                P.lk.resize(base + (size_t)S * 3, 1.0);
+            }
             for (size_t k = 0; k < cm.matched.size(); k++) {
-                double *dst = &P.lk[base + (size_t)cm.unique[k] * 3];
+                const size_t at = base + (size_t)cm.unique[k] * 3;
                 split(col[cm.matched[k]], ',', pl);
                 for (size_t j = 0; j < 3 && j < pl.size(); j++) {
+                    if (compact) { // pow(10, -x/10) of a non-negative integer x: the table entry x
+                        if (pl[j].empty() || pl[j][0] == '-' || !integer_field(pl[j], P.pl[at + j])) return false;
+                        continue;
+                    }
                     const double x = to_double(pl[j]);
                     switch (opt.lk_type) { // file.cpp:1719-1738
-                    case 2: dst[j] = std::pow(10.0, x); break;
-                    case 3: dst[j] = std::exp(x); break;
-                    case 4: dst[j] = std::pow(10.0, -x / 10.0); break;
-                    default: dst[j] = x; break;
+                    case 2: P.lk[at + j] = std::pow(10.0, x); break;
+                    case 3: P.lk[at + j] = std::exp(x); break;
+                    case 4: P.lk[at + j] = std::pow(10.0, -x / 10.0); break;
+                    default: P.lk[at + j] = x; break;
                     }
                 }
             }
+            P.flags.push_back(0);
             P.lines.push_back(rows[li]);
         }
+        return true;
     };
-    auto format_range = [&](Part &P) {
+    auto format_range = [&](Part &P, const BlockResults &R) {
         std::vector<sv> col;
         std::string &o = P.out;
         o.clear();
@@ -890,7 +1102,7 @@ bool run_lk(const LkOptions &opt, const PedRows &ped) {
         for (const sv row : P.lines) {
             split(row, '\t', col);
             o += "LK:GPP:FPP:FGT\t";
-            const bool failed = batch.status[v] != 0;
+            const bool failed = R.status[v] != 0;
             if (failed) {
                 P.warn += "Warning: this variant hasn't been calculated: \n";
                 P.warn.append(row);
@@ -905,7 +1117,7 @@ bool run_lk(const LkOptions &opt, const PedRows &ped) {
                 }
                 o += ':';
                 const size_t off = (v * S + cm.unique[k]) * 3;
-                put_calls(o, &batch.single[off], &batch.post[off], batch.gt[v * S + cm.unique[k]]);
+                put_calls(o, &R.single[off], &R.post[off], R.gt[v * S + cm.unique[k]]);
             }
             o += '\n';
             v++;
@@ -915,52 +1127,9 @@ bool run_lk(const LkOptions &opt, const PedRows &ped) {
     AsyncWriter writer(fout);
     writer.push(std::move(out)); // header
     out.clear();
-    std::vector<sv> block;
-    bool eof = false;
-    while (!eof && ok) {
-        double t0 = now();
-        block.clear();
-        sv line;
-        while (block.size() < kBatch) {
-            if (!in.next(line) || line.size() < 2) {
-                eof = true;
-                break;
-            }
-            block.push_back(line);
-        }
-        if (block.empty()) break;
-        g_stats.records += (long long)block.size();
-        run_parallel(n_threads, [&](int t) {
-            const size_t lo = block.size() * (size_t)t / n_threads, hi = block.size() * (size_t)(t + 1) / n_threads;
-            parse_range(parts[t], block.data() + lo, hi - lo);
-        });
-        size_t total = 0;
-        for (Part &P : parts) {
-            P.first = total;
-            total += P.lines.size();
-        }
-        // the LK driver calls the engine with Known = false, chrType = 0 (file.cpp:1751,1768,1785): flags stay 0
-        batch.lk.resize(total * S * 3);
-        batch.flags.assign(total, 0);
-        for (Part &P : parts)
-            if (!P.lines.empty()) std::memcpy(&batch.lk[P.first * S * 3], P.lk.data(), P.lk.size() * sizeof(double));
-        g_stats.parse_s += now() - t0;
-        if (total && (!engine_ready() || !batch.run(eng, opt.method, S, opt.num_burn_in, opt.num_rep, opt.seed, v_offset))) {
-            ok = false;
-            break;
-        }
-        t0 = now();
-        run_parallel(n_threads, [&](int t) { format_range(parts[t]); });
-        for (Part &P : parts) {
-            writer.push(std::move(P.out));
-            if (!P.warn.empty()) std::cout << P.warn << std::flush;
-            g_stats.failed += P.failed;
-        }
-        v_offset += (long long)total;
-        g_stats.computed += (long long)total;
-        g_stats.write_s += now() - t0;
-    }
-    if (!engine_ready()) ok = false; // an input without records still reports a pedigree the engine rejects
+    auto accept = [](sv line) { return line.size() < 2 ? 0 : 1; };
+    const PipelineSetup setup{&eng, &eng_start, S, opt.method, opt.num_burn_in, opt.num_rep, opt.seed, &writer};
+    bool ok = run_pipeline(in, setup, accept, parse_range, format_range);
     {
         const double t0 = now();
         const bool written = writer.close();

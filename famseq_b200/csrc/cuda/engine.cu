@@ -353,9 +353,9 @@ int fs_create(const fs_pedigree *ped, const fs_params *params, int device, fs_en
 int fs_create_multi(const fs_pedigree *ped, const fs_params *params, const int *devices, int ndev, fs_engine **out) {
     if (!ped || !out || !devices || ndev < 1) return fail(FS_E_ARG, "fs_create_multi: null argument or no device");
     *out = nullptr;
-    for (int a = 0; a < ndev; a++)
-        for (int b = 0; b < a; b++)
-            if (devices[a] == devices[b]) return fail(FS_E_ARG, "fs_create_multi: device listed twice");
+    // a device may be listed more than once: every entry gets its own pipeline (streams, buffers) on that GPU
+    for (int g = 0; g < ndev; g++)
+        if (devices[g] < 0) return fail(FS_E_ARG, "fs_create_multi: negative device");
     if (ndev == 1) return fs_create(ped, params, devices[0], out);
     // the front engine holds the host side (pedigree, tables, info); the parts own the GPUs
     fs_engine *front = nullptr;
@@ -363,7 +363,7 @@ int fs_create_multi(const fs_pedigree *ped, const fs_params *params, const int *
     if (rc != FS_OK) return rc;
     for (int g = 0; g < ndev; g++) {
         fs_engine *part = nullptr;
-        rc = devices[g] < 0 ? fail(FS_E_ARG, "fs_create_multi: negative device") : fs_create(ped, params, devices[g], &part);
+        rc = fs_create(ped, params, devices[g], &part);
         if (rc != FS_OK) {
             const std::string keep = g_last_error;
             fs_destroy(front);

@@ -10,7 +10,8 @@
 //   * the per-child vectors  K_c[a][b] = sum_l T_c[l][a][b] * lk_c[l]  are formed once and shared by the two
 //     posterior messages and by the sibs' anterior messages (the recursion re-derives them each time);
 //   * x/s for the three genotypes of a row shares one correctly rounded reciprocal (one Markstein
-//     correction step per quotient; operands outside the safe exponent range take the plain IEEE divide);
+//     correction step per quotient); a variant with an operand outside the safe exponent range, a failing row
+//     or an LRC gate that keeps the pedigree out is redone by the complete pass with plain IEEE divisions;
 //     tests/test_parity_gpu.py::test_nuclear_fast_path_is_bit_identical checks the result bit for bit;
 //   * the block's input tile ([TB][S][3] FP64, contiguous in HBM) arrives through one TMA bulk copy
 //     (cp.async.bulk + mbarrier) and the post / single / gt / status tiles leave through TMA bulk stores, so
@@ -105,12 +106,53 @@ struct OutRows {
     }
 };
 
-// marginal of one member: v = (m * l) * a, row sum == 0 fails the variant (family.cpp:1296-1314)
-__device__ __forceinline__ bool finish(const Row3 &ml, const Row3 &a, const OutRows &out, int col) {
+// ---- x[0..2] / s for the rows of one variant ------------------------------------------------------------------
+// Every row this kernel normalises has the form x0, x1, x2 >= 0, s = (x0 + x1) + x2, so x_i <= s.
+//   FAST = false: IEEE divisions.  Used by the complete ("exact") pass, which also evaluates every failure rule.
+//   FAST = true : one correctly rounded reciprocal per row and one Markstein correction per quotient (common.cuh,
+//                 div3), which IS the IEEE quotient when s and the x_i are normal numbers in [2^-900, 2^900] (ZEROS: or
+//                 exact zeros -- the chrX priors contain structural zeros).  Instead of guarding every division, the
+//                 fast pass only RECORDS (in `bad`) whether an operand ever left that range: two integer min/max on the
+//                 high words per row (non-negative doubles order like their high words; a negative, NaN or infinite
+//                 operand lands outside as well).  A variant with bad == true is redone by the exact pass, so nothing is
+//                 approximated; in range, both passes produce the same bytes (tests/test_parity_gpu.py,
+//                 test_nuclear_fast_path_is_bit_identical runs wide-exponent inputs through both).
+constexpr int kHiLo = (1023 - 900) << 20, kHiHi = (1023 + 900) << 20;
+template <bool FAST, bool ZEROS> struct Divider {
+    static constexpr bool fast = FAST;
+    bool bad = false;
+    __device__ __forceinline__ static int key(double x) {
+        const int h = __double2hiint(x);
+        if (!ZEROS) return h;
+        return (h | __double2loint(x)) == 0 ? kHiLo : h; // an exact zero divides exactly
+    }
+    __device__ __forceinline__ void check(double x0, double x1, double x2, double s) {
+        // x_i <= s, so the x_i need the lower bound only; s needs both (ZEROS: every x_i may be an exact zero, and so s)
+        bad |= (min(min(key(x0), key(x1)), key(x2)) < kHiLo) | ((unsigned)(__double2hiint(s) - kHiLo) > (unsigned)(kHiHi - kHiLo));
+    }
+    __device__ __forceinline__ void operator()(double x0, double x1, double x2, double s, double &q0, double &q1, double &q2) {
+        if (FAST) {
+            check(x0, x1, x2, s);
+            const double r = __drcp_rn(s);
+            const double a = __dmul_rn(x0, r), b = __dmul_rn(x1, r), c = __dmul_rn(x2, r);
+            q0 = __fma_rn(__fma_rn(-s, a, x0), r, a);
+            q1 = __fma_rn(__fma_rn(-s, b, x1), r, b);
+            q2 = __fma_rn(__fma_rn(-s, c, x2), r, c);
+        } else {
+            q0 = x0 / s;
+            q1 = x1 / s;
+            q2 = x2 / s;
+        }
+    }
+};
+
+// marginal of one member: v = (m * l) * a, row sum == 0 fails the variant (family.cpp:1296-1314).  In the fast pass a zero
+// (or any out-of-range) sum is caught by the divider instead.
+template <class Div> __device__ __forceinline__ bool finish(Div &div, const Row3 &ml, const Row3 &a, const OutRows &out, int col) {
     const double v0 = ml.v[0] * a.v[0], v1 = ml.v[1] * a.v[1], v2 = ml.v[2] * a.v[2];
     const double sum = (v0 + v1) + v2;
     double p0, p1, p2;
-    div3(v0, v1, v2, sum, p0, p1, p2);
+    div(v0, v1, v2, sum, p0, p1, p2);
     out.put(col, p0, p1, p2);
     return sum == 0.0;
 }
@@ -118,9 +160,9 @@ __device__ __forceinline__ bool finish(const Row3 &ml, const Row3 &a, const OutR
 // The peeling of a nuclear family; returns true when the reference would return false.  Rows are indexed by ROLE:
 // 0 father, 1 mother, 2.. children in ped order.  wf / wm = prior * lk of the founders (the numerators of their
 // individual-only posteriors: the same products, formed once).
-template <int NC, bool X>
+template <int NC, bool X, class Div>
 __device__ __forceinline__ bool peel(const NuclearParams &P, const VariantPriors &pr, const Row3 (&L)[NC + 2], const Row3 &wf, const Row3 &wm,
-                                     const int (&col)[NC + 2], const OutRows &out) {
+                                     const int (&col)[NC + 2], const OutRows &out, Div &div) {
     const RunConstants &C = P.C;
     // K[c][a][b] = sum_l (T_c[l][a][b] * lk_c[l])
     double K[NC][3][3];
@@ -171,14 +213,16 @@ __device__ __forceinline__ bool peel(const NuclearParams &P, const VariantPriors
     }
     bool failed = false;
     // every member's row sum is checked (the order of the members does not matter for the values)
-    failed |= finish(pl_f, prior_f, out, col[0]);
-    failed |= finish(pl_m, prior_m, out, col[1]);
+    failed |= finish(div, pl_f, prior_f, out, col[0]);
+    failed |= finish(div, pl_m, prior_m, out, col[1]);
 #pragma unroll
     for (int c = 0; c < NC; c++) {
         const int sel = P.male_child[c] ? K_TAB_XM : K_TAB_XF;
         Row3 ant;
 #pragma unroll
         for (int g = 0; g < 3; g++) {
+            // the reference starts both sums from 0.0; 0.0 + t == t bit for bit unless t is -0.0, which needs a negative
+            // likelihood -- and those variants belong to the complete pass, so the fast pass skips the two additions
             double over_m = 0.0;
 #pragma unroll
             for (int a = 0; a < 3; a++) {
@@ -197,25 +241,38 @@ __device__ __forceinline__ bool peel(const NuclearParams &P, const VariantPriors
                         }
                         term = term * sibs;
                     }
-                    over_f = over_f + term;
+                    over_f = (Div::fast && b == 0) ? term : over_f + term;
                 }
-                over_m = over_m + wm.v[a] * over_f;
+                over_m = (Div::fast && a == 0) ? wm.v[a] * over_f : over_m + wm.v[a] * over_f;
             }
             ant.v[g] = over_m;
         }
-        failed |= finish(L[2 + c], ant, out, col[2 + c]); // the posterior message of a childless member is (1, 1, 1): 1 * lk = lk
+        failed |= finish(div, L[2 + c], ant, out, col[2 + c]); // the posterior message of a childless member is (1, 1, 1): 1 * lk = lk
     }
     return failed;
 }
 
 // One variant: individual-only posterior, LRC gate, peeling, genotype calls -- from the thread's row of the input tile
 // into its rows of the output tiles (all in shared memory).  Everything in between lives in registers, indexed by role.
-template <int NC, bool PL, bool SINGLE>
-__device__ __forceinline__ void variant_thread(const NuclearParams &P, unsigned flag, const void *in_row, const double *__restrict__ lut,
-                                               double *post_row, double *single_row, uint8_t *gt_row, uint8_t *status) {
+//
+// FAST = false is the complete computation (every rule of the reference: failing rows, any -LRC value, the LRC gate
+// keeping the pedigree out).  FAST = true is the same arithmetic for the case that is nearly every variant -- default
+// -LRC 1, pedigree needed, nothing fails, every division in the divider's range -- without the tests for the others; it
+// returns true when the variant was not such a case, and the caller then runs the complete computation over it.
+template <int NC, bool PL, bool SINGLE, bool X, bool FAST>
+__device__ __forceinline__ bool variant_body(const NuclearParams &P, unsigned flag, const void *in_row, const double *__restrict__ lut,
+                                             double *post_row, double *single_row, uint8_t *gt_row, uint8_t *status) {
     constexpr int NR = NC + 2;
     const RunConstants &C = P.C;
-    const VariantPriors pr = select_priors(C, flag);
+    VariantPriors pr;
+    {   // prior[known] for females and autosomes, prior[2 + known] for males on chrX: per-thread constant-bank look-ups
+        const int known = flag & 1u;
+#pragma unroll
+        for (int g = 0; g < 3; g++) {
+            pr.a[g] = C.prior[known][g];
+            pr.m[g] = X ? C.prior[2 + known][g] : pr.a[g];
+        }
+    }
     int col[NR];
     bool male[NR];
     col[0] = P.col_father;
@@ -229,6 +286,7 @@ __device__ __forceinline__ void variant_thread(const NuclearParams &P, unsigned 
     }
     // individual-only posterior (family.cpp:1405-1499) and LRC gate (family.cpp:1140-1162)
     const OutRows out{post_row, gt_row};
+    Divider<FAST, X> div;
     Row3 L[NR], W[2]; // lk of every role; lk * prior of the founders (also their "anterior * lk" in the peeling)
     bool failed = C.unseq_fail[flag & 3u] != 0;
     bool pedigree_needed = false;
@@ -241,18 +299,33 @@ __device__ __forceinline__ void variant_thread(const NuclearParams &P, unsigned 
         if (r < 2) W[r].v[0] = w0, W[r].v[1] = w1, W[r].v[2] = w2;
         if (col[r] >= 0) {
             const double rs = (w0 + w1) + w2;
-            if (rs <= 0.0) failed = true;
+            if (!FAST && rs <= 0.0) failed = true;
             if (SINGLE) {
                 const int k = col[r] * 3;
-                div3(w0, w1, w2, rs, single_row[k], single_row[k + 1], single_row[k + 2]);
+                div(w0, w1, w2, rs, single_row[k], single_row[k + 1], single_row[k + 2]);
+            } else if (FAST) {
+                div.check(w0, w1, w2, rs); // a row sum <= 0 (or NaN) must not go unnoticed
             }
-            double big = 0.0;
-            if (big < L[r].v[0]) big = L[r].v[0];
-            if (big < L[r].v[1]) big = L[r].v[1];
-            if (big < L[r].v[2]) big = L[r].v[2];
             const double ls = (L[r].v[0] + L[r].v[1]) + L[r].v[2];
-            if (lrc_wants_pedigree(C.lrc, L[r].v[0], L[r].v[1], L[r].v[2], big, ls)) pedigree_needed = true;
+            if (FAST) {
+                // -LRC 1 and non-negative likelihoods (anything else is left to the complete pass): big / ls < 1 <=> big < ls,
+                // and since ls >= big, the sample is certain exactly when ls equals one of its three likelihoods
+                if (!((ls == L[r].v[0]) | (ls == L[r].v[1]) | (ls == L[r].v[2]))) pedigree_needed = true;
+            } else {
+                double big = 0.0;
+                if (big < L[r].v[0]) big = L[r].v[0];
+                if (big < L[r].v[1]) big = L[r].v[1];
+                if (big < L[r].v[2]) big = L[r].v[2];
+                if (lrc_wants_pedigree(C.lrc, L[r].v[0], L[r].v[1], L[r].v[2], big, ls)) pedigree_needed = true;
+            }
         }
+    }
+    if (FAST) {
+        peel<NC, X>(P, pr, L, W[0], W[1], col, out, div);
+        *status = 0;
+        // not this pass's case: an individual-only failure, a likelihood that is negative, NaN or out of the divider's range
+        // (the products inherit it), the LRC gate keeping the pedigree out, another -LRC value
+        return failed | div.bad | !pedigree_needed | (C.lrc != 1.0);
     }
     if (!failed) {
         if (!pedigree_needed) { // FPP := GPP (family.cpp:1164-1249); rare with the default -LRC 1
@@ -266,14 +339,12 @@ __device__ __forceinline__ void variant_thread(const NuclearParams &P, unsigned 
                     const double w0 = L[r].v[0] * (male[r] ? pr.m[0] : pr.a[0]);
                     const double w1 = L[r].v[1] * (male[r] ? pr.m[1] : pr.a[1]);
                     const double w2 = L[r].v[2] * (male[r] ? pr.m[2] : pr.a[2]);
-                    div3(w0, w1, w2, (w0 + w1) + w2, p0, p1, p2);
+                    div(w0, w1, w2, (w0 + w1) + w2, p0, p1, p2);
                 }
                 out.put(col[r], p0, p1, p2);
             }
-        } else if ((flag >> 1) & 1u) {
-            failed = peel<NC, true>(P, pr, L, W[0], W[1], col, out);
         } else {
-            failed = peel<NC, false>(P, pr, L, W[0], W[1], col, out);
+            failed = peel<NC, X>(P, pr, L, W[0], W[1], col, out, div);
         }
     }
     if (failed) { // the reference returns false: every sample of the variant is reported as NA
@@ -285,6 +356,25 @@ __device__ __forceinline__ void variant_thread(const NuclearParams &P, unsigned 
         for (int c = 0; c < S; c++) gt_row[c] = 255;
     }
     *status = failed ? 1 : 0;
+    return false;
+}
+
+// The complete computation, kept out of line: it runs for the few variants the fast pass hands over.
+template <int NC, bool PL, bool SINGLE>
+__device__ __noinline__ void variant_exact(const NuclearParams &P, unsigned flag, const void *in_row, const double *__restrict__ lut, double *post_row,
+                                           double *single_row, uint8_t *gt_row, uint8_t *status) {
+    if ((flag >> 1) & 1u)
+        variant_body<NC, PL, SINGLE, true, false>(P, flag, in_row, lut, post_row, single_row, gt_row, status);
+    else
+        variant_body<NC, PL, SINGLE, false, false>(P, flag, in_row, lut, post_row, single_row, gt_row, status);
+}
+
+template <int NC, bool PL, bool SINGLE>
+__device__ __forceinline__ void variant_thread(const NuclearParams &P, unsigned flag, const void *in_row, const double *__restrict__ lut,
+                                               double *post_row, double *single_row, uint8_t *gt_row, uint8_t *status) {
+    const bool redo = ((flag >> 1) & 1u) ? variant_body<NC, PL, SINGLE, true, true>(P, flag, in_row, lut, post_row, single_row, gt_row, status)
+                                         : variant_body<NC, PL, SINGLE, false, true>(P, flag, in_row, lut, post_row, single_row, gt_row, status);
+    if (redo) variant_exact<NC, PL, SINGLE>(P, flag, in_row, lut, post_row, single_row, gt_row, status);
 }
 
 // PL = compact input (uint16 Phred-scaled likelihoods + decode table), SINGLE = the caller wants the individual-only
@@ -310,9 +400,15 @@ __global__ void __launch_bounds__(TB, NC == 1 ? 896 / TB : 1) es_nuclear_kernel(
     const bool full = nv == TB; // full tiles go through TMA; the ragged last tile uses plain loads/stores
     const In *g_in = (PL ? reinterpret_cast<const In *>(B.pl) : reinterpret_cast<const In *>(B.lk)) + v0 * S3;
 
+    auto block_sync = [] { // a one-warp block needs no CTA barrier
+        if (TB == 32)
+            __syncwarp();
+        else
+            __syncthreads();
+    };
     if (full) {
         if (tid == 0) mbar_init(&bar, 1);
-        __syncthreads();
+        block_sync();
         if (tid == 0) {
             mbar_expect_tx(&bar, in_bytes);
             bulk_load(s_in, g_in, in_bytes, &bar);
@@ -325,14 +421,14 @@ __global__ void __launch_bounds__(TB, NC == 1 ? 896 / TB : 1) es_nuclear_kernel(
     if (full)
         mbar_wait(&bar, 0);
     else
-        __syncthreads();
+        block_sync();
 
     if (tid < nv)
         variant_thread<NC, PL, SINGLE>(P, flag, s_in + tid * S3, B.lut, s_post + tid * S3, s_single + tid * S3, s_gt + tid * S, s_status + tid);
 
     if (full) {
         fence_async_smem(); // make this thread's shared-memory writes visible to the TMA engine
-        __syncthreads();
+        block_sync();
         if (tid == 0) {
             bulk_store(B.post + v0 * S3, s_post, out_bytes);
             if (SINGLE) bulk_store(B.single + v0 * S3, s_single, out_bytes);
@@ -341,7 +437,7 @@ __global__ void __launch_bounds__(TB, NC == 1 ? 896 / TB : 1) es_nuclear_kernel(
             bulk_commit_and_wait_read(); // shared memory must stay alive until the engine has read it
         }
     } else {
-        __syncthreads();
+        block_sync();
         for (int k = tid; k < nv * S3; k += TB) {
             B.post[v0 * S3 + k] = s_post[k];
             if (SINGLE) B.single[v0 * S3 + k] = s_single[k];

@@ -2,25 +2,32 @@
 //
 // Replaces family::calPostProbMCMC + estGenoProb (src/family.cpp:1932-2096, :2098-2299) for large batches.  The
 // table-driven kernel of mcmc_kernel.cu spends ~220 instructions per Gibbs step, most of them decoding the pedigree
-// (descriptor words, dynamic 2-bit genotype fields, padded child loops), and it keeps its 48 N bytes of chain state in
-// global memory, which makes it HBM-bound (profiles/r1i).  Here the pedigree is known when the code is written:
-//   * a sweep is ONE basic block of ~50 instructions per member: parents, children and spouses are named registers,
-//     sex and founder cases are resolved at generation time, there is no descriptor, no loop over members or
-//     children and no branch, so ptxas interleaves the Philox rounds, the table look-ups and the FP64 chains of
-//     neighbouring members;
-//   * a genotype is kept as the byte offset of its table row (g * 128): a transmission look-up is one integer
-//     multiply-add and three LDS.64 with immediate offsets; consecutive full sibs share the look-up of their row;
-//   * per chain, 3 own factors (1e6 * prior * lk) and 3 Rao-Blackwell accumulators per member are placed in registers,
-//     in thread-private shared-memory columns, or in a block-private scratch that stays in L2 (own factors through a
-//     software prefetch queue, accumulators through red.global.add.f64); gibbs_jit_default_config() has the measured
-//     trade-offs.  The sweep loop causes no DRAM traffic.
-// The kernel carries the sweep twice, with the autosomal and with the chrX rules (a thread takes the pair of loops of
-// its variant).  The straight-line code covers what a sweep almost always is: weight sums that are positive normal
+// (descriptor words, dynamic 2-bit genotype fields, padded child loops), and it keeps its chain state in global memory.
+// Here the pedigree is known when the code is written: parents, children and spouses are named registers, sex and
+// founder cases are resolved at generation time, a genotype is kept as the byte offset of its table row (g * 128), a
+// transmission look-up is one integer multiply-add and three LDS.64 with immediate offsets.
+//
+// Round 2: CACHED FULL CONDITIONALS.  A member's three conditional weights depend on the current genotypes of its
+// parents, children and spouses only.  On sequencing data most chains sit in one state nearly all the time (a Gibbs step
+// changes the member's genotype in 8e-5 of the steps of the benchmark pedigrees, 2e-2 on TestData/loftest with 8 of 11
+// members unsequenced), so recomputing the weights in every step -- what the reference does, and what round 1's kernel
+// did at ~50 instructions, 23 of them FP64, and 14-17 shared-memory wavefronts per step -- is almost always redundant.
+// Every chain now keeps, per member, the normalised weights of the last evaluation (P0 and Q2 = 1 - P2 in registers or
+// thread-private shared-memory columns) and a dirty bit; a step is
+//        if (dirty) { close the run of the old weights; recompute; store; }        // rare, divergent
+//        draw: g = rd < P0 ? 0 : rd > Q2 ? 2 : 1;                                 // the reference's rule, family.cpp:2161-2173
+//        if (g changed) dirty |= {parents, children, spouses of the member};       // constant masks
+// ~33 instructions, 3 of them FP64, at most two LDS.  The draws are exactly the ones a recomputation would give: same
+// inputs, same instruction sequence, same weights.  Rao-Blackwellisation (family.cpp:2175-2178) adds the SAME normalised
+// weights once per sampling sweep for as long as they stay valid; the kernel adds n * P when the run of n sampling
+// sweeps ends instead of n times P (one rounding per run instead of n: differs from sweep-by-sweep accumulation by a few
+// ulps, far inside the 1e-9 parity tolerance; tests compare the two kernels to 1e-12 relative).
+// Accumulators, P1, P2 and the sweep index of the last evaluation live in a block-private scratch that stays in L2 and is
+// touched only when a run ends.
+// The kernel carries the sweep twice, with the autosomal and with the chrX rules (a thread takes the loop of its
+// variant).  The straight-line code covers what a sweep almost always is: weight sums that are positive normal
 // numbers.  Chains in which a sum leaves that range are marked (status 2) and redone by the table-driven kernel,
 // which the engine launches right behind this one (engine.cu) -- so nothing is approximated.
-// The arithmetic is written with explicit round-to-nearest intrinsics in the order of mcmc_kernel.cu, and the Philox
-// counters are the same: both kernels return the same bytes (tests/test_parity_gpu.py checks it), which is what makes
-// it safe to compile in the background and switch kernels in the middle of a run.
 #include <dlfcn.h>
 #include <nvrtc.h>
 #include <unistd.h>
@@ -135,91 +142,89 @@ std::vector<Member> decode(const McmcPlan &pl) {
     return m;
 }
 
-enum Place { REG, SMEM, GLOB };
-
-// Where the 3 own factors and the 3 accumulators of every member live.  Members are assigned in ped order: registers
-// first, then shared-memory rows, the rest in the block-private global scratch (own factors: read through a software
-// prefetch queue; accumulators: fire-and-forget red.global.add.f64).
+// Where the cached weights (P0, Q2 = 1 - P2) of every member live: the first n_p_reg members in registers, the others in
+// thread-private shared-memory columns.  Per member, six rows of the block-private global scratch hold the three
+// accumulators, P1, P2 and the sweep index of the last evaluation.
 struct Layout {
-    int n = 0;
-    std::vector<Place> lk_place, acc_place;
-    std::vector<int> lk_row, acc_row; // row (3-vector) in the shared-memory area or in the scratch
-    int smem_rows = 0, glob_rows = 0;
-    std::vector<int> lk_glob; // members whose own factors come from the scratch, in ped order
-    int depth = 1;            // prefetch distance, in such members
+    int n = 0, n_reg = 0, smem_pairs = 0;
+    std::vector<int> pair; // shared-memory pair index of the member, -1 = registers
 };
-
-// Members that go to the scratch are spread evenly over the sweep (so that a short prefetch queue covers the L2
-// latency and the reductions do not bunch up); of the others, the first n_reg sit in registers, the rest in shared memory.
-std::vector<Place> spread(int n, int n_reg, int n_smem) {
-    std::vector<Place> place(n, SMEM);
-    const int n_glob = std::max(0, n - n_reg - n_smem);
-    for (int i = 0; i < n; i++)
-        if ((long)(i + 1) * n_glob / n != (long)i * n_glob / n) place[i] = GLOB;
-    int left = n_reg;
-    for (int i = 0; i < n && left > 0; i++)
-        if (place[i] != GLOB) {
-            place[i] = REG;
-            left--;
-        }
-    return place;
-}
 
 Layout make_layout(int n, const GibbsJitConfig &cfg) {
     Layout L;
     L.n = n;
-    L.acc_place = spread(n, cfg.n_acc_reg, cfg.n_acc_smem);
-    L.lk_place = spread(n, cfg.n_lk_reg, cfg.n_lk_smem);
-    L.lk_row.assign(n, -1);
-    L.acc_row.assign(n, -1);
-    for (int i = 0; i < n; i++) {
-        if (L.acc_place[i] == SMEM) L.acc_row[i] = L.smem_rows++;
-        if (L.acc_place[i] == GLOB) L.acc_row[i] = L.glob_rows++;
-    }
-    for (int i = 0; i < n; i++) {
-        if (L.lk_place[i] == SMEM) L.lk_row[i] = L.smem_rows++;
-        if (L.lk_place[i] == GLOB) {
-            L.lk_row[i] = L.glob_rows++;
-            L.lk_glob.push_back(i);
-        }
-    }
-    L.depth = std::max(1, cfg.prefetch);
+    L.n_reg = std::max(0, std::min(n, cfg.n_p_reg));
+    L.pair.assign(n, -1);
+    for (int i = L.n_reg; i < n; i++) L.pair[i] = L.smem_pairs++;
     return L;
 }
 
-size_t smem_bytes(const Layout &L, int tb) { return (size_t)kTabBytes + (size_t)L.smem_rows * 3 * tb * 8; }
+constexpr int kScratchRows = 6; // A0 A1 A2 P1 P2 LAST
+size_t smem_bytes(const Layout &L, int tb) { return (size_t)kTabBytes + (size_t)L.smem_pairs * 2 * tb * 8; }
 
-std::string smem_ref(int row, int g) { return "sa[" + std::to_string(row * 3 + g) + " * TB]"; }
-std::string glob_ref(int row, int g) { return "wg + " + std::to_string(row * 3 + g) + " * TB"; }
+std::string p0_ref(const Layout &L, int i) { return L.pair[i] < 0 ? "P" + std::to_string(i) : "sa[" + std::to_string(L.pair[i] * 2) + " * TB]"; }
+std::string q2_ref(const Layout &L, int i) { return L.pair[i] < 0 ? "Q" + std::to_string(i) : "sa[" + std::to_string(L.pair[i] * 2 + 1) + " * TB]"; }
+std::string scratch_ref(int i, int k) { return "wg + " + std::to_string(i * kScratchRows + k) + " * TB"; }
+enum { ROW_A0 = 0, ROW_P1 = 3, ROW_P2 = 4, ROW_LAST = 5 };
 
-// One Gibbs step of member i (family.cpp:2113-2178 / :2195-2295), as straight-line code.
-// `row` names three variables that hold the member's transmission row T[.][mother][father] (loaded by emit_sweep,
-// shared by consecutive full sibs).
-// chrX sweeps (family.cpp:2183-2297): a member's own transmission comes from the table of its sex, a child's from the
-// table of the child's sex, and only males get the children factor.
+// Members whose weights depend on the genotype of member j: its parents (j is one of their children), its children (their
+// own transmission) and its spouses (co-parents of its children).  The chrX sweep skips the children factor of females,
+// so its true sets are subsets of these; a superset only costs an evaluation.
+std::vector<std::vector<int>> neighbours(const std::vector<Member> &M) {
+    const int n = (int)M.size();
+    std::vector<std::vector<int>> nb(n);
+    auto add = [&](int j, int who) {
+        if (who != j && std::find(nb[j].begin(), nb[j].end(), who) == nb[j].end()) nb[j].push_back(who);
+    };
+    for (int i = 0; i < n; i++) {
+        if (!M[i].founder) {
+            add(i, M[i].mother), add(i, M[i].father); // i changes -> its parents' children factors change
+            add(M[i].mother, i), add(M[i].father, i); // a parent changes -> i's own transmission changes
+        }
+        for (const Member::Link &l : M[i].links) add(i, l.other), add(l.other, i);
+    }
+    return nb;
+}
+
 const char *table_of(bool chrx, bool male) { return chrx ? (male ? "tXM" : "tXF") : "tA"; }
 
-void emit_member(std::ostringstream &o, const std::vector<Member> &M, const Layout &L, int i, bool accumulate, const std::string &row,
-                 bool chrx) {
+// One Gibbs step of member i (family.cpp:2113-2178 / :2195-2295).
+// chrX sweeps (family.cpp:2183-2297): a member's own transmission comes from the table of its sex, a child's from the
+// table of the child's sex, and only males get the children factor.
+void emit_member(std::ostringstream &o, const std::vector<Member> &M, const Layout &L, const std::vector<std::vector<int>> &nb, int i, bool chrx) {
     const Member &m = M[i];
-    o << "            { // member " << i << (m.founder ? " (founder" : " (child of ") ;
+    const int n = (int)M.size(), words = (n + 31) / 32;
+    const std::string dw = "D" + std::to_string(i / 32), bit = std::to_string(1u << (i % 32)) + "u";
+    const std::string P0 = p0_ref(L, i), Q2 = q2_ref(L, i);
+    o << "            // member " << i << (m.founder ? " (founder" : " (child of ");
     if (!m.founder) o << m.mother << " x " << m.father;
     o << (m.male ? ", male)\n" : ", not male)\n");
-    if (L.lk_place[i] == GLOB) {
-        const int G = (int)L.lk_glob.size();
-        const int k = (int)(std::find(L.lk_glob.begin(), L.lk_glob.end(), i) - L.lk_glob.begin());
-        const int slot = k % L.depth, ahead = L.lk_glob[(k + L.depth) % G];
-        o << "                double w0 = q" << slot << "_0, w1 = q" << slot << "_1, w2 = q" << slot << "_2;\n";
-        o << "                q" << slot << "_0 = __ldcg(" << glob_ref(L.lk_row[ahead], 0) << "); q" << slot << "_1 = __ldcg("
-          << glob_ref(L.lk_row[ahead], 1) << "); q" << slot << "_2 = __ldcg(" << glob_ref(L.lk_row[ahead], 2) << ");\n";
-    } else if (L.lk_place[i] == SMEM) {
-        o << "                double w0 = " << smem_ref(L.lk_row[i], 0) << ", w1 = " << smem_ref(L.lk_row[i], 1) << ", w2 = "
-          << smem_ref(L.lk_row[i], 2) << ";\n";
-    } else {
-        o << "                double w0 = W" << i << "_0, w1 = W" << i << "_1, w2 = W" << i << "_2;\n";
+    o << "            if (" << dw << " & " << bit << ") { // a neighbour changed since the weights were evaluated\n";
+    o << "                " << dw << " &= ~" << bit << ";\n";
+    // close the run of the old weights: they were valid in sweeps LAST .. sweep-1, of which n are sampling sweeps
+    o << "                { const double run = fmax(0.0, __dsub_rn(tD, fmax(__ldcg(" << scratch_ref(i, ROW_LAST) << "), first)));\n"
+      << "                  *(" << scratch_ref(i, ROW_A0) << ") = __dadd_rn(__ldcg(" << scratch_ref(i, ROW_A0) << "), __dmul_rn(run, " << P0 << "));\n"
+      << "                  *(" << scratch_ref(i, ROW_A0 + 1) << ") = __dadd_rn(__ldcg(" << scratch_ref(i, ROW_A0 + 1) << "), __dmul_rn(run, __ldcg("
+      << scratch_ref(i, ROW_P1) << ")));\n"
+      << "                  *(" << scratch_ref(i, ROW_A0 + 2) << ") = __dadd_rn(__ldcg(" << scratch_ref(i, ROW_A0 + 2) << "), __dmul_rn(run, __ldcg("
+      << scratch_ref(i, ROW_P2) << "))); }\n";
+    // own factor (1e6 * prior) * lk for founders, 1e6 * lk otherwise (family.cpp:2115-2126)
+    for (int g = 0; g < 3; g++) {
+        std::ostringstream lkx, base;
+        if (m.col >= 0)
+            lkx << "lkv[" << m.col * 3 + g << "]";
+        else
+            lkx << "1.0";
+        if (m.founder)
+            base << "__dmul_rn(1000000.0, " << (m.male ? "pm" : "pa") << g << ")";
+        else
+            base << "1000000.0";
+        o << "                double w" << g << " = __dmul_rn(" << base.str() << ", " << lkx.str() << ");\n";
     }
-    if (!m.founder) // transmission from the parents' current genotypes
-        o << "                w0 = __dmul_rn(w0, " << row << "_0); w1 = __dmul_rn(w1, " << row << "_1); w2 = __dmul_rn(w2, " << row << "_2);\n";
+    if (!m.founder) // transmission from the parents' current genotypes: entry g*9 + mother*3 + father
+        o << "                { const u32 ta = " << table_of(chrx, m.male) << " + o" << m.mother << " * 3u + o" << m.father << ";\n"
+          << "                  w0 = __dmul_rn(w0, lds64(ta)); w1 = __dmul_rn(w1, lds64(ta + " << 9 * kRow << ")); w2 = __dmul_rn(w2, lds64(ta + "
+          << 18 * kRow << ")); }\n";
     for (const Member::Link &l : m.links) {
         if (chrx && !m.male) break; // family.cpp:2230-2257
         const char *tA = table_of(chrx, l.child_male);
@@ -233,72 +238,32 @@ void emit_member(std::ostringstream &o, const std::vector<Member> &M, const Layo
               << ")); w2 = __dmul_rn(w2, lds64(ta + " << 6 * kRow << ")); }\n";
     }
     o << "                const double sum = __dadd_rn(__dadd_rn(w0, w1), w2);\n";
+    // The straight-line code assumes a positive normal sum with exponent in [-963, 963) (no sign test, Newton reciprocal);
+    // `worst` records whether that ever failed, in which case the chain is redone by the table-driven kernel.
+    o << "                worst = max(worst, (u32)__double2hiint(sum) - 0x03c00000u);\n";
+    o << "                const double inv = newton_reciprocal(sum);\n";
+    o << "                const double p0 = __dmul_rn(w0, inv), p1 = __dmul_rn(w1, inv), p2 = __dmul_rn(w2, inv);\n";
+    o << "                " << P0 << " = p0; " << Q2 << " = __dsub_rn(1.0, p2);\n";
+    o << "                *(" << scratch_ref(i, ROW_P1) << ") = p1; *(" << scratch_ref(i, ROW_P2) << ") = p2; *(" << scratch_ref(i, ROW_LAST) << ") = tD;\n";
+    o << "            }\n";
+    // the draw (family.cpp:2161-2173): rd < w0 -> 0, rd > 1 - w2 -> 2, else 1, on the normalised weights
+    o << "            {\n";
     if ((i & 3) == 0) o << "                philox((u32)sweep, " << (i >> 2) << "u, gv_lo, gv_hi, k0, k1, r0, r1, r2, r3);\n";
     // (u + 0.5) * 2^-32 without an int-to-double conversion: 1 + u * 2^-32 assembled from bits, then one exact subtraction
     o << "                const double rd = __dsub_rn(__hiloint2double((int)(0x3ff00000u | (r" << (i & 3) << " >> 12)), (int)(r" << (i & 3)
       << " << 20)), 0x1.ffffffffp-1);\n";
-    o << "                const double thr = __dmul_rn(rd, sum);\n";
-    // The straight-line code assumes a positive normal sum with exponent in [-963, 963) (no sign test, Newton reciprocal);
-    // `worst` records whether that ever failed, in which case the chain is redone by the table-driven kernel.
-    o << "                worst = max(worst, (u32)__double2hiint(sum) - 0x03c00000u);\n";
-    o << "                o" << i << " = (thr < w0) ? 0u : ((thr > __dsub_rn(sum, w2)) ? " << 2 * kRow << "u : " << kRow << "u);\n";
-    if (accumulate) {
-        o << "                const double inv = newton_reciprocal(sum);\n";
-        for (int g = 0; g < 3; g++) {
-            const std::string term = "__dmul_rn(w" + std::to_string(g) + ", inv)";
-            if (L.acc_place[i] == SMEM)
-                o << "                " << smem_ref(L.acc_row[i], g) << " = __dadd_rn(" << smem_ref(L.acc_row[i], g) << ", " << term << ");\n";
-            else if (L.acc_place[i] == GLOB)
-                o << "                atomicAdd(" << glob_ref(L.acc_row[i], g) << ", " << term << ");\n";
-            else
-                o << "                A" << i << "_" << g << " = __dadd_rn(A" << i << "_" << g << ", " << term << ");\n";
-        }
-    }
+    o << "                const u32 g = (rd < " << P0 << ") ? 0u : ((rd > " << Q2 << ") ? " << 2 * kRow << "u : " << kRow << "u);\n";
+    std::vector<unsigned> mask(words, 0u);
+    for (int j : nb[i]) mask[j / 32] |= 1u << (j % 32);
+    o << "                const u32 changed = (g != o" << i << ") ? 0xffffffffu : 0u;\n";
+    for (int w = 0; w < words; w++)
+        if (mask[w]) o << "                D" << w << " |= changed & " << mask[w] << "u;\n";
+    o << "                o" << i << " = g;\n";
     o << "            }\n";
 }
 
-// One sweep over the members in ped order.  A non-founder's own factor needs the row T[g][mother][father], g = 0..2
-// (entry g*9 + mother*3 + father): full sibs that follow each other before either parent is updated again share one
-// look-up -- three shared-memory loads saved per sib, and shared-memory bandwidth is what bounds this kernel.
-void emit_sweep(std::ostringstream &o, const std::vector<Member> &M, const Layout &L, bool accumulate, bool chrx, const char *tag) {
-    const int n = (int)M.size();
-    std::vector<int> version(n, 0);
-    struct Row {
-        int mother, father, vm, vf;
-        bool male;
-        std::string name;
-    };
-    std::vector<Row> rows;
-    for (int i = 0; i < n; i++) {
-        std::string row;
-        if (!M[i].founder) {
-            const int mo = M[i].mother, fa = M[i].father;
-            for (const Row &r : rows)
-                if (r.mother == mo && r.father == fa && r.vm == version[mo] && r.vf == version[fa] && (!chrx || r.male == M[i].male))
-                    row = r.name;
-            if (row.empty()) {
-                row = std::string("T") + tag + std::to_string(i);
-                o << "            const u32 a" << row << " = " << table_of(chrx, M[i].male) << " + o" << mo << " * 3u + o" << fa << ";\n";
-                o << "            const double " << row << "_0 = lds64(a" << row << "), " << row << "_1 = lds64(a" << row << " + " << 9 * kRow << "), "
-                  << row << "_2 = lds64(a" << row << " + " << 18 * kRow << ");\n";
-                rows.push_back({mo, fa, version[mo], version[fa], M[i].male, row});
-            }
-        }
-        emit_member(o, M, L, i, accumulate, row, chrx);
-        version[i]++;
-    }
-}
-
-// End of a sweep: the loads in flight belong to the first members of the next sweep; put them where it expects them.
-void emit_queue_rotation(std::ostringstream &o, const Layout &L) {
-    const int G = (int)L.lk_glob.size(), D = L.depth;
-    if (G == 0 || G % D == 0) return;
-    o << "            { // prefetch queue: slot j of the next sweep is slot (j + " << G % D << ") % " << D << " of this one\n";
-    for (int j = 0; j < D; j++)
-        for (int g = 0; g < 3; g++) o << "                const double t" << j << "_" << g << " = q" << (G + j) % D << "_" << g << ";\n";
-    for (int j = 0; j < D; j++)
-        for (int g = 0; g < 3; g++) o << "                q" << j << "_" << g << " = t" << j << "_" << g << ";\n";
-    o << "            }\n";
+void emit_sweep(std::ostringstream &o, const std::vector<Member> &M, const Layout &L, const std::vector<std::vector<int>> &nb, bool chrx) {
+    for (int i = 0; i < (int)M.size(); i++) emit_member(o, M, L, nb, i, chrx);
 }
 
 } // namespace
@@ -306,43 +271,32 @@ void emit_queue_rotation(std::ostringstream &o, const Layout &L) {
 GibbsJitConfig gibbs_jit_default_config(const McmcParams &P) {
     const int n = P.plan.n;
     GibbsJitConfig c;
-    // Two warps per SM sub-partition: 256 chains per SM, up to 255 registers each.  Measured on the 40-member pedigree
-    // (profiles/jit_sweep*.sh): registers are the only free storage -- a shared-memory row costs LDS bandwidth (the unit
-    // that bounds the kernel), an accumulator in L2 costs three reductions (the L2 sustains ~6.5e11 FP64 reductions/s
-    // per GPU), own factors in L2 cost three loads.  So: accumulators in registers as far as they go (the step itself
-    // needs ~124 + n), a sixth of the shared-memory rows for more accumulators, the rest of them for own factors, and
-    // whatever is left in L2.
+    // Two warps per SM sub-partition: 256 chains per SM, up to 255 registers each.  A chain needs ~70 registers for the step
+    // itself, one per member for the genotypes and four per member whose cached weights (P0, Q2) sit in registers; the
+    // other members' pairs go to thread-private shared-memory columns (16 bytes per member and chain).  When even that does
+    // not fit (very large pedigrees) the block shrinks.
     c.tb = 256;
     c.blocks = 1;
-    c.prefetch = 2;
-    const int reg_rows = std::max(0, (254 - (124 + n)) / 6);
-    const int smem_rows = (int)((kSmemPerBlockMax - kTabBytes) / ((size_t)24 * c.tb));
-    c.n_acc_reg = std::min(n, reg_rows);
-    c.n_lk_reg = std::min(n, reg_rows - c.n_acc_reg);
-    c.n_acc_smem = std::min(n - c.n_acc_reg, smem_rows / 6);
-    c.n_lk_smem = std::min(n - c.n_lk_reg, smem_rows - c.n_acc_smem);
-    if (c.n_acc_reg == n && c.n_lk_reg == n) // small pedigree, everything in registers: more than one block per SM
-        c.blocks = std::max(1, std::min(4, 65536 / (c.tb * (70 + n + 12 * n))));
+    c.n_p_reg = std::max(0, std::min(n, (250 - (84 + n)) / 4));
+    while (c.tb > 32 && kTabBytes + (size_t)(n - c.n_p_reg) * 16 * c.tb > kSmemPerBlockMax) c.tb -= 32;
+    if (c.n_p_reg == n) // small pedigree, everything in registers: more than one block per SM
+        c.blocks = std::max(1, std::min(4, 65536 / (c.tb * (80 + 5 * n))));
     c.tb = env_int("FAMSEQ_JIT_TB", c.tb);
     c.blocks = std::max(1, env_int("FAMSEQ_JIT_BLOCKS", c.blocks));
-    c.prefetch = std::max(1, env_int("FAMSEQ_JIT_PF", c.prefetch));
-    c.n_acc_reg = std::min(n, std::max(0, env_int("FAMSEQ_JIT_RACC", c.n_acc_reg)));
-    c.n_acc_smem = std::min(n - c.n_acc_reg, std::max(0, env_int("FAMSEQ_JIT_SACC", c.n_acc_smem)));
-    c.n_lk_reg = std::min(n, std::max(0, env_int("FAMSEQ_JIT_RLK", c.n_lk_reg)));
-    c.n_lk_smem = std::min(n - c.n_lk_reg, std::max(0, env_int("FAMSEQ_JIT_SLK", c.n_lk_smem)));
+    c.n_p_reg = std::min(n, std::max(0, env_int("FAMSEQ_JIT_PREG", c.n_p_reg)));
     return c;
 }
 
 std::string gibbs_jit_source(const McmcParams &P, const GibbsJitConfig &cfg) {
     const RunConstants &C = P.C;
     const std::vector<Member> M = decode(P.plan);
-    const int n = (int)M.size(), S = C.s;
+    const int n = (int)M.size(), S = C.s, words = (n + 31) / 32;
     const Layout L = make_layout(n, cfg);
+    const std::vector<std::vector<int>> nb = neighbours(M);
     std::ostringstream o;
     o << "// generated by famseq_b200 (gibbs_jit.cu) for one pedigree: " << n << " members, " << S << " input columns\n";
-    o << "// layout: " << cfg.tb << " chains per block; accumulators " << cfg.n_acc_reg << " reg / " << cfg.n_acc_smem << " smem / "
-      << n - cfg.n_acc_reg - cfg.n_acc_smem << " L2; own factors " << cfg.n_lk_reg << " reg / " << cfg.n_lk_smem << " smem / "
-      << L.lk_glob.size() << " L2 (prefetch " << L.depth << ")\n";
+    o << "// layout: " << cfg.tb << " chains per block; cached weights of " << L.n_reg << " members in registers, of " << L.smem_pairs
+      << " in shared memory; accumulators and run bookkeeping in a block-private L2 scratch\n";
     o << "#define TB " << cfg.tb << "\n#define NCOL " << S << "\n";
     o << kPrelude;
     o << "__constant__ u64 TAB_BITS[81] = {";
@@ -362,14 +316,14 @@ std::string gibbs_jit_source(const McmcParams &P, const GibbsJitConfig &cfg) {
       << "             u64 seed, i64 v_offset, double *scratch, int n_tiles) {\n"
       << "    extern __shared__ __align__(16) unsigned char smem_raw[];\n"
       << "    double *s_tab = (double *)smem_raw;              // [81][" << kCopies << "]\n"
-      << "    double *s_vec = s_tab + 81 * " << kCopies << ";           // [" << L.smem_rows << " * 3][TB] thread-private columns\n"
+      << "    double *s_vec = s_tab + 81 * " << kCopies << ";           // [" << L.smem_pairs << " * 2][TB] thread-private columns: P0, Q2\n"
       << "    const int tid = threadIdx.x, lane = tid & 31;\n"
       << "    for (int e = tid; e < 81 * " << kCopies << "; e += TB) s_tab[e] = __longlong_as_double((i64)TAB_BITS[e / " << kCopies << "]);\n"
       << "    __syncthreads();\n"
       << "    u32 tab_addr = (u32)__cvta_generic_to_shared(s_tab) + (u32)(lane & " << (kCopies - 1) << ") * 8u;\n"
       << "    asm volatile(\"\" : \"+r\"(tab_addr) :: \"memory\"); // table reads stay below the barrier\n"
       << "    double *sa = s_vec + tid;\n"
-      << "    double *wg = scratch + (size_t)blockIdx.x * " << std::max(1, L.glob_rows) * 3 << " * TB + tid; // [row][g][TB], block-private\n"
+      << "    double *wg = scratch + (size_t)blockIdx.x * " << n * kScratchRows << " * TB + tid; // [member][A0 A1 A2 P1 P2 LAST][TB], block-private\n"
       << "    const u32 k0 = (u32)seed, k1 = (u32)(seed >> 32);\n"
       << "    const double lrc = __longlong_as_double((i64)" << bits(C.lrc) << ");\n"
       << "    (void)sa; (void)wg;\n\n"
@@ -419,33 +373,17 @@ std::string gibbs_jit_source(const McmcParams &P, const GibbsJitConfig &cfg) {
       << "        const u32 tA = tab_addr, tXF = tab_addr + " << 27 * kRow << "u, tXM = tab_addr + " << 54 * kRow << "u;\n"
       << "        (void)tA; (void)tXF; (void)tXM;\n"
       << "        u32 worst = 0u;\n\n"
-      << "        // chain state: own factors (1e6 * prior) * lk for founders, 1e6 * lk otherwise (family.cpp:2115-2126)\n";
+      << "        // chain state: nothing evaluated yet (every member dirty), empty runs\n";
     for (int i = 0; i < n; i++) {
-        const Member &m = M[i];
-        for (int g = 0; g < 3; g++) {
-            std::ostringstream lkx, base;
-            if (m.col >= 0)
-                lkx << "lkv[" << m.col * 3 + g << "]";
-            else
-                lkx << "1.0";
-            if (m.founder)
-                base << "__dmul_rn(1000000.0, " << (m.male ? "pm" : "pa") << g << ")";
-            else
-                base << "1000000.0";
-            const std::string value = "__dmul_rn(" + base.str() + ", " + lkx.str() + ")";
-            if (L.lk_place[i] == GLOB)
-                o << "        *(" << glob_ref(L.lk_row[i], g) << ") = " << value << ";\n";
-            else if (L.lk_place[i] == SMEM)
-                o << "        " << smem_ref(L.lk_row[i], g) << " = " << value << ";\n";
-            else
-                o << "        const double W" << i << "_" << g << " = " << value << ";\n";
-            if (L.acc_place[i] == GLOB)
-                o << "        *(" << glob_ref(L.acc_row[i], g) << ") = 0.0;\n";
-            else if (L.acc_place[i] == SMEM)
-                o << "        " << smem_ref(L.acc_row[i], g) << " = 0.0;\n";
-            else
-                o << "        double A" << i << "_" << g << " = 0.0;\n";
-        }
+        if (L.pair[i] < 0)
+            o << "        double P" << i << " = 0.0, Q" << i << " = 0.0;\n";
+        else
+            o << "        " << p0_ref(L, i) << " = 0.0; " << q2_ref(L, i) << " = 0.0;\n";
+        for (int k = 0; k < kScratchRows; k++) o << "        *(" << scratch_ref(i, k) << ") = 0.0;\n";
+    }
+    for (int w = 0; w < words; w++) {
+        const int members = std::min(32, n - 32 * w);
+        o << "        u32 D" << w << " = " << (members >= 32 ? 0xffffffffu : ((1u << members) - 1u)) << "u;\n";
     }
     o << "        const u64 gv = (u64)(v_offset + v);\n"
       << "        const u32 gv_lo = (u32)gv, gv_hi = (u32)(gv >> 32);\n"
@@ -455,51 +393,30 @@ std::string gibbs_jit_source(const McmcParams &P, const GibbsJitConfig &cfg) {
         if ((i & 3) == 0) o << "        philox(0u, " << (i >> 2) << "u, gv_lo, gv_hi, k0, k1, r0, r1, r2, r3);\n";
         o << "        u32 o" << i << " = (r" << (i & 3) << " % 3u) * " << kRow << "u;\n";
     }
-    if (!L.lk_glob.empty()) {
-        const int G = (int)L.lk_glob.size();
-        o << "        // prefetch queue of own factors: " << L.depth << " member(s) ahead\n";
-        for (int j = 0; j < L.depth; j++) {
-            const int row = L.lk_row[L.lk_glob[j % G]];
-            o << "        double q" << j << "_0 = __ldcg(" << glob_ref(row, 0) << "), q" << j << "_1 = __ldcg(" << glob_ref(row, 1) << "), q" << j
-              << "_2 = __ldcg(" << glob_ref(row, 2) << ");\n";
-        }
-    }
-    o << "\n        int sweep = 1;\n"
-      << "        const int last = burn + rep;\n"
+    o << "\n        const int last = burn + rep;\n"
+      << "        const double first = (double)(burn + 1); // first sampling sweep: runs are counted from here (family.cpp:2069-2080)\n"
+      << "        double tD = 1.0;                          // the sweep index as a double\n"
       << "        if (!chrx) {\n"
-      << "        for (; sweep <= burn; sweep++) { // burn-in: no accumulation\n";
-    emit_sweep(o, M, L, false, false, "b");
-    emit_queue_rotation(o, L);
+      << "        for (int sweep = 1; sweep <= last; sweep++, tD = __dadd_rn(tD, 1.0)) {\n";
+    emit_sweep(o, M, L, nb, false);
     o << "        }\n"
-      << "        for (; sweep <= last; sweep++) { // sampling sweeps, Rao-Blackwellised (family.cpp:2175-2178)\n";
-    emit_sweep(o, M, L, true, false, "s");
-    emit_queue_rotation(o, L);
-    o << "        }\n"
-      << "        } else { // the same two loops with the chrX rules\n"
-      << "        for (; sweep <= burn; sweep++) {\n";
-    emit_sweep(o, M, L, false, true, "xb");
-    emit_queue_rotation(o, L);
-    o << "        }\n"
-      << "        for (; sweep <= last; sweep++) {\n";
-    emit_sweep(o, M, L, true, true, "xs");
-    emit_queue_rotation(o, L);
+      << "        } else { // the same loop with the chrX rules\n"
+      << "        for (int sweep = 1; sweep <= last; sweep++, tD = __dadd_rn(tD, 1.0)) {\n";
+    emit_sweep(o, M, L, nb, true);
     o << "        }\n"
       << "        }\n"
       << "        if (worst >= 0x78600000u) { status[v] = 2; continue; } // a sum left the fast range: redo with the table-driven kernel\n\n"
-      << "        // postProb = genoFry / numRep, not renormalised; a row summing to <= 0 fails (family.cpp:2082-2092)\n"
+      << "        // postProb = genoFry / numRep, not renormalised; a row summing to <= 0 fails (family.cpp:2082-2092).\n"
+      << "        // tD is last + 1 here: the weights still standing close their runs.\n"
       << "        const double nrep = (double)rep;\n";
     for (int i = 0; i < n; i++) {
-        o << "        {\n";
-        for (int g = 0; g < 3; g++) {
-            std::string a;
-            if (L.acc_place[i] == GLOB)
-                a = "__ldcg(" + glob_ref(L.acc_row[i], g) + ")";
-            else if (L.acc_place[i] == SMEM)
-                a = smem_ref(L.acc_row[i], g);
-            else
-                a = "A" + std::to_string(i) + "_" + std::to_string(g);
-            o << "            const double p" << g << " = __ddiv_rn(" << a << ", nrep);\n";
-        }
+        o << "        {\n"
+          << "            const double run = fmax(0.0, __dsub_rn(tD, fmax(__ldcg(" << scratch_ref(i, ROW_LAST) << "), first)));\n"
+          << "            const double p0 = __ddiv_rn(__dadd_rn(__ldcg(" << scratch_ref(i, ROW_A0) << "), __dmul_rn(run, " << p0_ref(L, i) << ")), nrep);\n"
+          << "            const double p1 = __ddiv_rn(__dadd_rn(__ldcg(" << scratch_ref(i, ROW_A0 + 1) << "), __dmul_rn(run, __ldcg(" << scratch_ref(i, ROW_P1)
+          << "))), nrep);\n"
+          << "            const double p2 = __ddiv_rn(__dadd_rn(__ldcg(" << scratch_ref(i, ROW_A0 + 2) << "), __dmul_rn(run, __ldcg(" << scratch_ref(i, ROW_P2)
+          << "))), nrep);\n";
         o << "            if (__dadd_rn(__dadd_rn(p0, p1), p2) <= 0.0) failed = true;\n";
         if (M[i].col >= 0) {
             const int c = M[i].col;
@@ -665,7 +582,7 @@ int gibbs_jit_load(const McmcParams &P, const GibbsJitConfig &cfg, const std::st
     GibbsJitKernel *k = new GibbsJitKernel();
     k->cfg = cfg;
     k->smem = smem;
-    k->glob_rows = L.glob_rows;
+    k->glob_rows = L.n * kScratchRows;
     auto cuda_err = [&](cudaError_t e, const char *what) {
         err = std::string("Gibbs JIT: ") + what + ": " + cudaGetErrorString(e);
         gibbs_jit_unload(k);
@@ -697,8 +614,8 @@ int gibbs_jit_build(const McmcParams &P, const GibbsJitConfig &cfg, std::string 
     if (rc != FS_OK) return rc;
     if (const char *v = std::getenv("FAMSEQ_JIT_VERBOSE"))
         if (v[0] == '1')
-            std::fprintf(stderr, "[famseq] Gibbs JIT tb=%d blocks=%d acc %d reg/%d smem, own factors %d reg/%d smem, prefetch %d, smem=%zu\n%s\n",
-                         cfg.tb, cfg.blocks, cfg.n_acc_reg, cfg.n_acc_smem, cfg.n_lk_reg, cfg.n_lk_smem, cfg.prefetch, smem, log.c_str());
+            std::fprintf(stderr, "[famseq] Gibbs JIT tb=%d blocks=%d cached weights of %d members in registers, smem=%zu\n%s\n", cfg.tb,
+                         cfg.blocks, cfg.n_p_reg, smem, log.c_str());
     return FS_OK;
 }
 
@@ -716,8 +633,8 @@ cudaError_t gibbs_jit_launch(GibbsJitKernel *k, const BatchPtrs &B, int burn, in
     if (n_tiles64 > 0x7fffffff) return cudaErrorInvalidValue;
     int n_tiles = (int)n_tiles64;
     const int grid = (int)std::min<int64_t>(n_tiles64, (int64_t)sm_count * k->blocks_per_sm);
-    double *scratch = nullptr; // own factors [grid][member][g][tb], stream-ordered
-    cudaError_t rc = cudaMallocAsync(&scratch, (size_t)grid * std::max(1, k->glob_rows) * 3 * tb * sizeof(double), stream);
+    double *scratch = nullptr; // accumulators and run bookkeeping [grid][member][6][tb], stream-ordered
+    cudaError_t rc = cudaMallocAsync(&scratch, (size_t)grid * std::max(1, k->glob_rows) * tb * sizeof(double), stream);
     if (rc != cudaSuccess) return rc;
     const double *lk = B.lk;
     const uint8_t *flags = B.flags;

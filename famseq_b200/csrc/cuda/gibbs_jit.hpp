@@ -1,7 +1,7 @@
 // gibbs_jit.hpp -- pedigree-specialised Gibbs sampler: the engine writes CUDA C++ for ONE pedigree (every member,
 // parent and child index a literal, the member loop unrolled, genotypes in named registers), compiles it for
-// sm_100a with NVRTC when the first large MCMC batch arrives and launches the resulting kernel.  Semantics, random
-// stream and rounding are those of the table-driven kernel in mcmc_kernel.cu (same bytes out); see gibbs_jit.cu.
+// sm_100a with NVRTC when the first large MCMC batch arrives and launches the resulting kernel.  Semantics and random
+// stream are those of the table-driven kernel in mcmc_kernel.cu (same chains; posteriors equal to a few ulps); see gibbs_jit.cu.
 #pragma once
 
 #include <string>
@@ -10,17 +10,15 @@
 
 namespace famseq {
 
-// Per chain, the sampler keeps 3 own factors and 3 accumulators per member.  Members are placed in ped order: the
-// first n_*_reg in registers, the next n_*_smem in shared memory, the rest in a block-private global scratch (L2).
+// Per chain and member the sampler caches the normalised conditional weights of the last evaluation (P0 and 1 - P2): for
+// the first n_p_reg members in registers, for the others in thread-private shared-memory columns (see gibbs_jit.cu).
 struct GibbsJitConfig {
-    int tb = 0;          // chains (threads) per block
-    int blocks = 1;      // resident blocks per SM the register budget is sized for
-    int n_acc_reg = 0, n_acc_smem = 0;
-    int n_lk_reg = 0, n_lk_smem = 0;
-    int prefetch = 1;    // own factors read from the scratch are requested this many members ahead
+    int tb = 0;      // chains (threads) per block
+    int blocks = 1;  // resident blocks per SM the register budget is sized for
+    int n_p_reg = 0; // members whose cached weights live in registers
 };
 
-// Layout heuristic (overridable with FAMSEQ_JIT_TB / _BLOCKS / _RACC / _SACC / _RLK / _SLK / _PF).
+// Layout heuristic (overridable with FAMSEQ_JIT_TB / _BLOCKS / _PREG).
 GibbsJitConfig gibbs_jit_default_config(const McmcParams &P);
 
 std::string gibbs_jit_source(const McmcParams &P, const GibbsJitConfig &cfg);

@@ -98,7 +98,8 @@ void fs_destroy(fs_engine *e);
  * fs_run_pl call is cut into `ndev` contiguous slices of variants -- slice g = [g V/ndev, (g+1) V/ndev) on devices[g],
  * one host thread and one copy/compute pipeline per GPU -- and every GPU writes its slice of the caller's ordered
  * host buffers.  There is no inter-GPU collective; Gibbs streams are keyed by the global variant index, so the bytes
- * do not depend on ndev.  The *_device entry points need a single-GPU engine (FS_E_ARG otherwise). */
+ * do not depend on ndev.  A device may be listed more than once (each entry is an independent pipeline on that GPU).
+ * The *_device entry points need a single-GPU engine (FS_E_ARG otherwise). */
 int fs_create_multi(const fs_pedigree *ped, const fs_params *params, const int *devices, int ndev, fs_engine **out);
 
 /* Thread-local text of the last error raised on the calling thread. */

@@ -503,9 +503,14 @@ static double rng_uniform(rng_t *r, int sweep, int member) {
  * The generated CUDA Gibbs kernel hands a chain back to the table-driven kernel when a sum leaves the positive normal
  * range [2^-963, 2^963); the tests use this probe to check that it does so exactly when it must. */
 static double g_sum_min = 0, g_sum_max = 0;
+static long long g_steps = 0, g_changes = 0; /* Gibbs steps / steps that changed the member's genotype, same call */
 void fso_mcmc_sum_range(double out[2]) {
     out[0] = g_sum_min;
     out[1] = g_sum_max;
+}
+void fso_mcmc_change_count(long long out[2]) {
+    out[0] = g_steps;
+    out[1] = g_changes;
 }
 
 /* one sweep over all individuals in ped order */
@@ -539,12 +544,15 @@ static void gibbs_sweep(const fam_t *f, int *cur, double *acc, int known, int ch
         else
             for (int g = 0; g < 3; g++) w[g] = w[g] / s;
         double rd = rng_uniform(rng, sweep, i);
+        const int before = cur[i];
         if (rd < w[0])
             cur[i] = 0;
         else if (rd > (1.0 - w[2]))
             cur[i] = 2;
         else
             cur[i] = 1;
+        g_steps++;
+        g_changes += cur[i] != before;
         for (int g = 0; g < 3; g++) acc[i * 3 + g] = acc[i * 3 + g] + w[g];
     }
 }
@@ -603,6 +611,7 @@ int fso_run(int method, int N, const int *ped_id, const int *ped_mid, const int 
     if (method == FSO_MCMC && rng_kind == FSO_RNG_LIBC && seed >= 0) srand((unsigned)seed);
     g_sum_min = INFINITY;
     g_sum_max = -INFINITY;
+    g_steps = g_changes = 0;
 
     for (int64_t v = 0; v < V; v++) {
         const int known = flags[v] & 1, chrx = (flags[v] >> 1) & 1;

@@ -64,6 +64,8 @@ void fso_pl_table(double *out, int n);
 
 /* Test probe: {min, max} of the Gibbs weight sums met during the last fso_run(FSO_MCMC) call (over all its variants). */
 void fso_mcmc_sum_range(double out[2]);
+/* Test probe: {Gibbs steps, steps that changed the member's genotype} of the last fso_run(FSO_MCMC) call. */
+void fso_mcmc_change_count(long long out[2]);
 
 /* Philox4x32-10 block, exposed so the host/CUDA implementations can be checked against it. */
 void fso_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);

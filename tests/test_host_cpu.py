@@ -124,12 +124,12 @@ def test_synthetic_generator_is_sliceable():
 @pytest.mark.parametrize("name", ["trio", "ped14", "ped40"])
 def test_generated_gibbs_kernel_compiles_for_sm_100a(name):
     """The pedigree-specialised Gibbs kernel (csrc/cuda/gibbs_jit.cu): the engine writes CUDA C++ for the pedigree and
-    NVRTC compiles it to an sm_100a cubin; neither step needs a device.  Every member must appear as a straight-line
-    block, and the hot loop must not spill more than a few registers."""
+    NVRTC compiles it to an sm_100a cubin; neither step needs a device.  Every member must appear as a block of its
+    own, and the hot loop must not spill more than a few registers."""
     ped = synth.PEDIGREES[name]()
     with fs.Engine(ped.ids, ped.mids, ped.fids, ped.genders, ped.sequenced_cols(), device=-1) as e:
         src, _ = e.gibbs_kernel()
-        assert src.count("// member ") == 4 * ped.n  # burn-in and sampling copies of the sweep, autosomal and chrX rules
+        assert src.count("// member ") == 2 * ped.n  # one copy of the sweep with the autosomal, one with the chrX rules
         assert 'extern "C" __global__' in src and "famseq_gibbs" in src
         log, cubin_bytes = e.gibbs_kernel(compile=True)
     assert cubin_bytes > 0
@@ -207,7 +207,7 @@ def test_compact_entry_has_no_cpu_fallback_either():
 
 def test_multi_device_argument_checks():
     ped = synth.trio()
-    for devices in ([], [0, 0], [1, 2, 1]):
+    for devices in ([], [-1], [0, -2]):
         with pytest.raises(fs.FamSeqError) as ei:
             fs.Engine(ped.ids, ped.mids, ped.fids, ped.genders, ped.sequenced_cols(), device=devices)
         assert ei.value.code == -1

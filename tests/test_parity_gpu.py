@@ -13,7 +13,7 @@ import pytest
 import famseq_b200 as fs
 from famseq_b200 import synth
 from oracle import oracle as O
-from tests.util import REL_TOL, CasePed, assert_parity, golden_cases, load_case, rel_err
+from tests.util import REL_TOL, CasePed, assert_parity, assert_same_chains, golden_cases, load_case, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -232,8 +232,9 @@ def test_mcmc_same_stream_as_oracle(pedname, V, burn, rep):
                                                      ("ped40", None, 600, 10, 150), ("ped100", None, 300, 10, 60)])
 def test_mcmc_specialised_kernel_returns_the_same_bytes(pedname, cols, V, burn, rep, monkeypatch):
     """The Gibbs kernel the engine generates and compiles for one pedigree (gibbs_jit.cu) against the table-driven
-    kernel: same Philox stream, same operation order, hence identical bytes -- autosomes and chrX, Known or not,
-    partially sequenced pedigrees, -LRC gating and the oracle on top."""
+    kernel: same Philox stream, same weights, hence the same chains -- autosomes and chrX, Known or not, partially
+    sequenced pedigrees, -LRC gating and the oracle on top.  (Round 2: the generated kernel caches the conditional
+    weights and adds n * P per run of n unchanged sweeps, so the posteriors agree to a few ulps, no longer bit for bit.)"""
     ped = synth.PEDIGREES[pedname]()
     cols = ped.sequenced_cols() if cols is None else cols
     lk, fl = synth.synth_likelihoods(synth._mk([(i, 0, 0, 1) for i in range(1, len(cols) + 1)]), V, seed=77, x_fraction=0.3)
@@ -246,16 +247,14 @@ def test_mcmc_specialised_kernel_returns_the_same_bytes(pedname, cols, V, burn, 
     with engine_for(ped, cols) as e:
         jit = e.run(fs.MCMC, lk, fl, burn=burn, rep=rep, seed=99, v_offset=5)
         assert e.info()["jit_launches"] >= 1
-    assert np.array_equal(jit.status, generic.status) and np.array_equal(jit.gt, generic.gt)
-    assert np.array_equal(jit.single, generic.single, equal_nan=True)
-    assert np.array_equal(jit.post, generic.post, equal_nan=True)
+    assert_same_chains(jit, generic, f"mcmc-jit/{pedname}")
     want = O.run(ped, cols, lk, fl, method=O.MCMC, burn=burn, rep=rep, rng=O.RNG_PHILOX, seed=99, v_offset=5)
     assert_parity(jit, want, 1e-9, f"mcmc-jit/{pedname}")
 
 
 def test_mcmc_background_compile_switches_kernels_without_changing_results(monkeypatch):
     """Default mode: a large batch starts the compile on a worker thread, batches run on the table-driven kernel until
-    the cubin is ready, later ones on the specialised kernel; the bytes do not depend on which kernel ran."""
+    the cubin is ready, later ones on the specialised kernel; the results do not depend on which kernel ran (to a few ulps)."""
     import time
     ped = synth.half_sibs()
     lk, fl = synth.synth_likelihoods(ped, 4000, seed=5, x_fraction=0.2)
@@ -268,7 +267,7 @@ def test_mcmc_background_compile_switches_kernels_without_changing_results(monke
             time.sleep(0.5)
             again = e.run(fs.MCMC, lk, fl, burn=10, rep=100, seed=3)
         assert e.info()["jit_launches"] >= 1, "the specialised kernel never became ready"
-    assert np.array_equal(first.post, again.post, equal_nan=True) and np.array_equal(first.gt, again.gt)
+    assert_same_chains(first, again, "background compile")
 
 
 def test_mcmc_converges_to_exact_bn():
@@ -447,6 +446,6 @@ def test_random_pedigree_all_methods(seed, monkeypatch):
             ok = w_es["status"] == 0
             assert np.array_equal(es.status, w_es["status"]) and np.array_equal(es.post[ok], w_es["post"][ok]), f"random {seed} ES jit={jit}"
         results[jit] = (mc, es)
-    assert np.array_equal(results["0"][0].post, results["1"][0].post, equal_nan=True)
+    assert_same_chains(results["0"][0], results["1"][0], f"random {seed} MCMC kernels")
     if results["0"][1] is not None:
         assert np.array_equal(results["0"][1].post, results["1"][1].post, equal_nan=True)
