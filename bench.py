@@ -293,12 +293,15 @@ def time_device_path(torch, dist, fs, eng, wl: Workload, rank, world, steps, war
     return ms / steps, launches, clk.summary(), failed, keep
 
 
-def time_e2e_path(torch, dist, eng, wl: Workload, rank, world, steps, warmup, keep, compact=True, single=False):
+def time_e2e_path(torch, dist, eng, wl: Workload, rank, world, steps, warmup, keep, compact=True, single=False, phred=False):
     """The reference-facing call on pinned HOST buffers, H2D and D2H inside the timed region: fs_run_pl() (compact input,
-    post + gt + status out) or fs_run() (FP64 likelihoods in, single as well out)."""
+    post + gt + status out), fs_run() (FP64 likelihoods in, single as well out) or fs_run_pl_phred() (compact input,
+    posteriors as the six Phred digits the reference prints, 4 bytes per value)."""
     V, S = wl.variants, len(wl.ped.sequenced_cols())
     h_in, h_fl = (keep["h_pl"] if compact else keep["h_lk"]), keep["h_fl"]
-    h_post = torch.empty((V, S, 3), dtype=torch.float64).pin_memory()
+    h_post = (torch.empty((V, S, 3), dtype=torch.int32) if phred else torch.empty((V, S, 3), dtype=torch.float64)).pin_memory()
+    fixes = np.zeros(1 << 16, dtype=[("index", np.int64), ("p", np.float64)])
+    n_fixes = [0]
     h_single = torch.empty((V, S, 3), dtype=torch.float64).pin_memory() if single else None
     h_gt = torch.empty((V, S), dtype=torch.uint8).pin_memory()
     h_st = torch.empty(V, dtype=torch.uint8).pin_memory()
@@ -306,6 +309,10 @@ def time_e2e_path(torch, dist, eng, wl: Workload, rank, world, steps, warmup, ke
     call = eng.run_pl_raw if compact else eng.run_raw
 
     def step():
+        if phred:
+            n_fixes[0] = eng.run_pl_phred_raw(mid, V, h_in.data_ptr(), h_fl.data_ptr(), h_post.data_ptr(), None, h_gt.data_ptr(), h_st.data_ptr(),
+                                              fixes, len(fixes), burn=wl.burn, rep=wl.rep, seed=SEED, v_offset=rank * V)
+            return
         call(mid, V, h_in.data_ptr(), h_fl.data_ptr(), h_post.data_ptr(), h_single.data_ptr() if single else None, h_gt.data_ptr(),
              h_st.data_ptr(), burn=wl.burn, rep=wl.rep, seed=SEED, v_offset=rank * V)
 
@@ -324,9 +331,20 @@ def time_e2e_path(torch, dist, eng, wl: Workload, rank, world, steps, warmup, ke
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         sec = float(t.item())
     # the device-resident and the host path must have produced the same bytes
-    same = bool(torch.equal(keep["d_post"].cpu(), h_post) and torch.equal(keep["d_gt"].cpu(), h_gt) and torch.equal(keep["d_st"].cpu(), h_st))
+    same = bool(torch.equal(keep["d_gt"].cpu(), h_gt) and torch.equal(keep["d_st"].cpu(), h_st))
+    if phred:  # every code must print what the reference prints for the device path's double (checked on the first 20 000 variants)
+        import famseq_b200 as fs
+        from oracle import oracle as O
+
+        n = min(V, 20000) * S * 3
+        codes = h_post.numpy().view(np.uint32).reshape(-1)[:n]
+        exact = keep["d_post"][:min(V, 20000)].cpu().numpy().reshape(-1)
+        decided = (codes >> 30) != 3
+        same = same and n_fixes[0] <= len(fixes) and all(fs.phred_text(int(c)) == O.phred_text(float(x)) for c, x in zip(codes[decided], exact[decided]))
+    else:
+        same = same and bool(torch.equal(keep["d_post"].cpu(), h_post))
     h2d = h_in.numel() * h_in.element_size() + h_fl.numel()
-    d2h = h_post.numel() * 8 + (h_single.numel() * 8 if single else 0) + h_gt.numel() + h_st.numel()
+    d2h = h_post.numel() * h_post.element_size() + (h_single.numel() * 8 if single else 0) + h_gt.numel() + h_st.numel() + (8 + 16 * min(n_fixes[0], len(fixes)) if phred else 0)
     return sec / steps, h2d, d2h, same
 
 
@@ -536,10 +554,13 @@ def main():
                                          "traffic": traffic * args.variants if traffic else None, "algorithmic_bytes_per_variant": ab}}
         # headline e2e: the compact entry on pinned host buffers (2 B per likelihood up, post + gt + status down)
         e2e_s, h2d, d2h, same = time_e2e_path(torch, dist, eng, wl, rank, world, e2e_steps, args.warmup, keep, compact=True, single=False)
+        # ... and with the posteriors as the reference prints them (Phred, six digits), 4 bytes per value
+        e2ep_s, h2dp, d2hp, samep = time_e2e_path(torch, dist, eng, wl, rank, world, e2e_steps, args.warmup, keep, compact=True, single=False, phred=True)
         del keep, want_post, want_gt
     torch.cuda.empty_cache()
     ceiling = host_copy_ceiling(torch, dist, world, h2d, d2h)
     ceiling64 = host_copy_ceiling(torch, dist, world, h2d64, d2h64)
+    ceilingp = host_copy_ceiling(torch, dist, world, h2dp, d2hp)
     value = world * args.variants / (ms_step * 1e-3)
     achieved = algorithmic_bytes(3) * args.variants / (ms_step * 1e-3) / 1e9
     tr = profile_json("es_trio_traffic.json").get("canonical", {})
@@ -561,6 +582,11 @@ def main():
                           "ms_per_step": e2e64_s * 1e3, "api": "fs_run() on pinned host buffers: FP64 likelihoods up, post + single + gt + status down",
                           "matches_device_path": same64, "host_copy_ceiling_gbs": ceiling64,
                           "frac_of_host_copy_ceiling": world * (h2d64 + d2h64) / e2e64_s / 1e9 / ceiling64},
+        "e2e_phred": {"value": world * args.variants / e2ep_s, "unit": UNIT, "h2d_bytes_per_step": h2dp, "d2h_bytes_per_step": d2hp,
+                      "ms_per_step": e2ep_s * 1e3, "api": "fs_run_pl_phred() on pinned host buffers: uint16 PL + flags up; FPP as the six Phred digits the "
+                      "reference prints (uint32 codes, device-encoded, exact: values next to a rounding boundary come back as doubles), gt, status down",
+                      "codes_print_what_the_reference_prints": samep, "host_copy_ceiling_gbs": ceilingp,
+                      "frac_of_host_copy_ceiling": world * (h2dp + d2hp) / e2ep_s / 1e9 / ceilingp},
         "layouts": layouts,
         "gpu_launches": launches, "clocks": clocks, "failed_variants": failed,
         "fp64_peak_tflops_measured": fp64_peak, "host_cores_of_rank0": len(cores) if cores else None,
@@ -679,6 +705,8 @@ def main():
             out[f"{name}_variants_per_s"] = sub[key]["value"]
             if "roofline" in sub[key]:
                 out[f"{name}_roofline_frac"] = sub[key]["roofline"]["frac"]
+    out["e2e_phred_variants_per_s"] = out["e2e_phred"]["value"]
+    out["e2e_fp64_full_variants_per_s"] = out["e2e_fp64_full"]["value"]
     for tag, L in layouts.items():
         out[f"es_trio_{tag}_variants_per_s"] = L["value"]
         out[f"es_trio_{tag}_roofline_frac"] = L["roofline"]["frac"]

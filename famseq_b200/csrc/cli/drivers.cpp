@@ -11,7 +11,7 @@
 // the host with libm and takes the FP64 entry.  Phred encoding (log10) stays on the host so that the text is
 // byte-identical to the reference's.
 #include "drivers.hpp"
-#include "format_g.hpp"
+#include "../host/format_g.hpp"
 
 #include <algorithm>
 #include <atomic>
@@ -190,15 +190,23 @@ void put_phred(std::string &out, double p) {
         put_number(out, std::fabs(v));
 }
 
-void put_calls(std::string &out, const double *single, const double *post, uint8_t gt) {
-    put_phred(out, single[0]); out += ',';
-    put_phred(out, single[1]); out += ',';
-    put_phred(out, single[2]); out += ':';
-    put_phred(out, post[0]); out += ',';
-    put_phred(out, post[1]); out += ',';
-    put_phred(out, post[2]); out += ':';
-    out += gt == 0 ? "0/0\t" : (gt == 1 ? "0/1\t" : "1/1\t"); // file.cpp:750-761: anything but 0 and 1 prints 1/1
+struct BlockResults;
+
+// One Phred column from a device code; the few codes the device left open are looked up (exact double) and formatted here.
+void put_phred_code(std::string &out, uint32_t code, int64_t index, const fs_phred_fix *fixes, size_t n_fixes) {
+    char buf[16];
+    const int n = fs_phred_text(code, buf);
+    if (n >= 0) {
+        out.append(buf, (size_t)n);
+        return;
+    }
+    const fs_phred_fix *end = fixes + n_fixes;
+    const fs_phred_fix *it = std::lower_bound(fixes, end, index, [](const fs_phred_fix &f, int64_t i) { return f.index < i; });
+    put_phred(out, it != end && it->index == index ? it->p : std::numeric_limits<double>::quiet_NaN());
 }
+
+// GPP, FPP and FGT of one sample (file.cpp:702-761); `off` is the position of the sample's first value in the block
+void put_calls(std::string &out, const BlockResults &R, size_t off, uint8_t gt);
 
 const char *kFormatLines =
     "##FORMAT=<ID=FPP,Number=G,Type=Integer,Description=\"Normalized, Phred-scaled for posterior probability calculated by FamSeqPro\">\n"
@@ -294,18 +302,22 @@ struct Engine {
 struct HostBuffers {
     size_t cap = 0; // variants
     uint16_t *pl = nullptr;
-    double *lk = nullptr, *post = nullptr, *single = nullptr;
+    uint32_t *post32 = nullptr, *single32 = nullptr; // Phred codes (compact blocks)
+    double *lk = nullptr, *post = nullptr, *single = nullptr; // FP64 blocks: allocated when the first one comes along
     uint8_t *flags = nullptr, *gt = nullptr, *status = nullptr;
+    std::vector<fs_phred_fix> fixes; // values of a compact block the host formats itself, sorted by index
     ~HostBuffers() { release(); }
     void release() {
         fs_free_pinned(pl);
+        fs_free_pinned(post32);
+        fs_free_pinned(single32);
         fs_free_pinned(lk);
         fs_free_pinned(post);
         fs_free_pinned(single);
         fs_free_pinned(flags);
         fs_free_pinned(gt);
         fs_free_pinned(status);
-        pl = nullptr, lk = post = single = nullptr, flags = gt = status = nullptr, cap = 0;
+        pl = nullptr, post32 = single32 = nullptr, lk = post = single = nullptr, flags = gt = status = nullptr, cap = 0;
     }
     bool reserve(size_t variants, size_t S, bool want_lk) {
         if (variants > cap) {
@@ -313,15 +325,21 @@ struct HostBuffers {
             cap = std::max(variants, kBatch);
             const size_t n3 = std::max<size_t>(cap * S * 3, 1);
             pl = static_cast<uint16_t *>(fs_alloc_pinned(n3 * sizeof(uint16_t)));
-            post = static_cast<double *>(fs_alloc_pinned(n3 * sizeof(double)));
-            single = static_cast<double *>(fs_alloc_pinned(n3 * sizeof(double)));
+            post32 = static_cast<uint32_t *>(fs_alloc_pinned(n3 * sizeof(uint32_t)));
+            single32 = static_cast<uint32_t *>(fs_alloc_pinned(n3 * sizeof(uint32_t)));
             flags = static_cast<uint8_t *>(fs_alloc_pinned(cap));
             gt = static_cast<uint8_t *>(fs_alloc_pinned(std::max<size_t>(cap * S, 1)));
             status = static_cast<uint8_t *>(fs_alloc_pinned(cap));
-            if (!pl || !post || !single || !flags || !gt || !status) return false;
+            if (!pl || !post32 || !single32 || !flags || !gt || !status) return false;
         }
-        if (want_lk && !lk) lk = static_cast<double *>(fs_alloc_pinned(std::max<size_t>(cap * S * 3, 1) * sizeof(double)));
-        return !want_lk || lk;
+        if (want_lk && !lk) {
+            const size_t n3 = std::max<size_t>(cap * S * 3, 1);
+            lk = static_cast<double *>(fs_alloc_pinned(n3 * sizeof(double)));
+            post = static_cast<double *>(fs_alloc_pinned(n3 * sizeof(double)));
+            single = static_cast<double *>(fs_alloc_pinned(n3 * sizeof(double)));
+            if (!lk || !post || !single) return false;
+        }
+        return true;
     }
 };
 
@@ -357,6 +375,7 @@ struct Block {
     size_t total = 0;
     long long v_offset = 0;
     bool compact = true;
+    size_t n_fixes = 0;
     HostBuffers buf;
 };
 
@@ -475,9 +494,37 @@ class EngineStart {
 //                                   likelihood field is not an integer (the range is then parsed again in FP64)
 //   format(part, results): writes part.out / part.warn / part.failed from the engine's results of the part's block
 struct BlockResults {
-    const double *post, *single;
+    const double *post, *single;       // FP64 blocks
+    const uint32_t *post32, *single32; // compact blocks: Phred codes from the device
+    const fs_phred_fix *fixes;         // ... and the few values it left to the host, sorted by index
+    size_t n_fixes;
     const uint8_t *gt, *status;
+    bool compact;
 };
+void put_calls(std::string &out, const BlockResults &R, size_t off, uint8_t gt) {
+    static const char sep[3] = {',', ',', ':'};
+    if (R.compact) {
+        for (int g = 0; g < 3; g++) {
+            put_phred_code(out, R.single32[off + g], (int64_t)(off + g) + FS_PHRED_FIX_SINGLE, R.fixes, R.n_fixes);
+            out += sep[g];
+        }
+        for (int g = 0; g < 3; g++) {
+            put_phred_code(out, R.post32[off + g], (int64_t)(off + g), R.fixes, R.n_fixes);
+            out += sep[g];
+        }
+    } else {
+        for (int g = 0; g < 3; g++) {
+            put_phred(out, R.single[off + g]);
+            out += sep[g];
+        }
+        for (int g = 0; g < 3; g++) {
+            put_phred(out, R.post[off + g]);
+            out += sep[g];
+        }
+    }
+    out += gt == 0 ? "0/0\t" : (gt == 1 ? "0/1\t" : "1/1\t"); // file.cpp:750-761: anything but 0 and 1 prints 1/1
+}
+
 struct PipelineSetup {
     Engine *engine;
     EngineStart *start;
@@ -583,10 +630,25 @@ bool run_pipeline(Lines &in, const PipelineSetup &ps, Accept accept, Parse parse
                     else
                         std::memcpy(b->buf.lk + off, P.lk.data(), n3 * sizeof(double));
                 }
-                const int rc = b->compact ? fs_run_pl(ps.engine->h, ps.method, (int64_t)b->total, b->buf.pl, b->buf.flags, ps.burn, ps.rep, ps.seed,
-                                                      b->v_offset, b->buf.post, b->buf.single, b->buf.gt, b->buf.status)
-                                          : fs_run(ps.engine->h, ps.method, (int64_t)b->total, b->buf.lk, b->buf.flags, ps.burn, ps.rep, ps.seed,
-                                                   b->v_offset, b->buf.post, b->buf.single, b->buf.gt, b->buf.status);
+                int rc;
+                if (b->compact) { // integer PL fields up, Phred codes down: 2 and 4 bytes per value instead of 8 and 8
+                    int64_t n_fixes = 0;
+                    b->buf.fixes.resize(std::max<size_t>(b->buf.fixes.size(), 4096));
+                    rc = fs_run_pl_phred(ps.engine->h, ps.method, (int64_t)b->total, b->buf.pl, b->buf.flags, ps.burn, ps.rep, ps.seed, b->v_offset,
+                                         b->buf.post32, b->buf.single32, b->buf.gt, b->buf.status, b->buf.fixes.data(), (int64_t)b->buf.fixes.size(), &n_fixes);
+                    if (rc == FS_OK && n_fixes > (int64_t)b->buf.fixes.size()) { // more exceptions than room (NaN-ridden input): once more with room for all
+                        b->buf.fixes.resize((size_t)n_fixes);
+                        rc = fs_run_pl_phred(ps.engine->h, ps.method, (int64_t)b->total, b->buf.pl, b->buf.flags, ps.burn, ps.rep, ps.seed, b->v_offset,
+                                             b->buf.post32, b->buf.single32, b->buf.gt, b->buf.status, b->buf.fixes.data(), (int64_t)b->buf.fixes.size(), &n_fixes);
+                    }
+                    b->n_fixes = rc == FS_OK ? (size_t)n_fixes : 0;
+                    std::sort(b->buf.fixes.begin(), b->buf.fixes.begin() + (long)b->n_fixes,
+                              [](const fs_phred_fix &x, const fs_phred_fix &y) { return x.index < y.index; });
+                    g_stats.phred_fixes += (long long)b->n_fixes;
+                } else {
+                    rc = fs_run(ps.engine->h, ps.method, (int64_t)b->total, b->buf.lk, b->buf.flags, ps.burn, ps.rep, ps.seed, b->v_offset, b->buf.post,
+                                b->buf.single, b->buf.gt, b->buf.status);
+                }
                 g_stats.engine_s += now() - t0;
                 g_stats.kernel_ms += fs_last_kernel_ms(ps.engine->h);
                 g_stats.batches++;
@@ -609,7 +671,8 @@ bool run_pipeline(Lines &in, const PipelineSetup &ps, Accept accept, Parse parse
         Block *b = nullptr;
         while (format_q.pop(b)) {
             const double t0 = now();
-            const BlockResults res{b->buf.post, b->buf.single, b->buf.gt, b->buf.status};
+            const BlockResults res{b->buf.post, b->buf.single, b->buf.post32, b->buf.single32, b->buf.fixes.data(), b->compact ? b->n_fixes : 0,
+                                   b->buf.gt, b->buf.status, b->compact};
             run_parallel(n_threads, [&](int t) { format(b->parts[t], res); });
             for (Part &P : b->parts) {
                 ps.writer->push(std::move(P.out));
@@ -637,10 +700,10 @@ bool run_pipeline(Lines &in, const PipelineSetup &ps, Accept accept, Parse parse
 void emit_stats() {
     if (!std::getenv("FAMSEQ_STATS")) return;
     std::fprintf(stderr,
-                 "{\"records\": %lld, \"computed\": %lld, \"failed\": %lld, \"batches\": %lld, \"compact_batches\": %lld, \"parse_s\": %.4f, "
+                 "{\"records\": %lld, \"computed\": %lld, \"failed\": %lld, \"batches\": %lld, \"compact_batches\": %lld, \"phred_fixes\": %lld, \"parse_s\": %.4f, "
                  "\"engine_s\": %.4f, \"kernel_ms\": %.3f, \"write_s\": %.4f, \"read_s\": %.4f, \"start_wait_s\": %.4f, "
                  "\"drain_s\": %.4f, \"total_s\": %.4f}\n",
-                 g_stats.records, g_stats.computed, g_stats.failed, g_stats.batches, g_stats.compact_batches, g_stats.parse_s, g_stats.engine_s,
+                 g_stats.records, g_stats.computed, g_stats.failed, g_stats.batches, g_stats.compact_batches, g_stats.phred_fixes, g_stats.parse_s, g_stats.engine_s,
                  g_stats.kernel_ms, g_stats.write_s, g_stats.read_s, g_stats.start_wait_s, g_stats.drain_s, g_stats.total_s);
 }
 
@@ -971,7 +1034,7 @@ bool run_vcf(const VcfOptions &opt, const PedRows &ped) {
                     o += ':';
                 }
                 const size_t off = (v * S + cm.unique[k]) * 3;
-                put_calls(o, &R.single[off], &R.post[off], R.gt[v * S + cm.unique[k]]);
+                put_calls(o, R, off, R.gt[v * S + cm.unique[k]]);
             }
             o += '\n';
             v++;
@@ -1117,7 +1180,7 @@ bool run_lk(const LkOptions &opt, const PedRows &ped) {
                 }
                 o += ':';
                 const size_t off = (v * S + cm.unique[k]) * 3;
-                put_calls(o, &R.single[off], &R.post[off], R.gt[v * S + cm.unique[k]]);
+                put_calls(o, R, off, R.gt[v * S + cm.unique[k]]);
             }
             o += '\n';
             v++;

@@ -26,7 +26,8 @@ bool run_lk(const LkOptions &opt, const PedRows &ped);
 // Run statistics of the last driver call (written to stderr as one JSON line when FAMSEQ_STATS is set).
 struct RunStats {
     long long records = 0, computed = 0, failed = 0, batches = 0;
-    long long compact_batches = 0; // engine calls that shipped integer PL fields as they stand (fs_run_pl)
+    long long compact_batches = 0; // engine calls that shipped integer PL fields up and Phred codes down (fs_run_pl_phred)
+    long long phred_fixes = 0;     // values of those the device left to the host formatter
     double parse_s = 0, engine_s = 0, kernel_ms = 0, write_s = 0, total_s = 0;
     double read_s = 0, start_wait_s = 0, drain_s = 0; // input file read, waiting for fs_create, waiting for the writer
 };

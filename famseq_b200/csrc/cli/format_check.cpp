@@ -4,7 +4,7 @@
 #include <cinttypes>
 #include <cstdlib>
 
-#include "format_g.hpp"
+#include "../host/format_g.hpp"
 
 namespace {
 uint64_t s_state;

@@ -7,12 +7,14 @@
 #include <memory>
 #include <cstdio>
 #include <cstring>
+#include <limits>
 #include <new>
 #include <string>
 #include <thread>
 #include <vector>
 
 #include "../../../include/famseq_b200.h"
+#include "../host/format_g.hpp"
 #include "../host/pedigree.hpp"
 #include "es_jit.hpp"
 #include "gibbs_jit.hpp"
@@ -45,6 +47,7 @@ struct DeviceChunk {
     cudaEvent_t k0 = nullptr, k1 = nullptr;
     double *lk = nullptr, *post = nullptr, *single = nullptr; // lk / single are allocated when first needed
     uint16_t *pl = nullptr;
+    uint32_t *post32 = nullptr, *single32 = nullptr; // Phred codes (fs_run_pl_phred), allocated when first needed
     uint8_t *flags = nullptr, *gt = nullptr, *status = nullptr;
     int64_t capacity = 0; // variants
     int64_t in_flight = 0;
@@ -57,6 +60,13 @@ struct BatchIo {
     const uint8_t *flags = nullptr;
     double *post = nullptr, *single = nullptr;
     uint8_t *gt = nullptr, *status = nullptr;
+    // compact output (fs_run_pl_phred): Phred codes instead of doubles, exceptions with their exact doubles
+    uint32_t *post_phred = nullptr, *single_phred = nullptr;
+    fs_phred_fix *fixes = nullptr;
+    int64_t fix_capacity = 0;
+    int64_t *n_fixes = nullptr;
+    int64_t index_base = 0; // position of this batch's first value in the caller's arrays (multi-device slices)
+    bool phred() const { return post_phred != nullptr; }
 };
 
 // Pedigree-specialised Gibbs kernel (gibbs_jit.cu).  FAMSEQ_MCMC_JIT: 0 = never, 1 = compile at the first MCMC batch and
@@ -129,6 +139,9 @@ struct fs_engine {
     std::vector<double> pl_table;          // lut[pl] = pow(10, -pl/10), host libm (file.cpp:588-590)
     double *d_pl_table = nullptr;          // the same on the device, uploaded at the first fs_run_pl
     unsigned long long *d_fixups = nullptr; // chains redone by the table-driven kernel after the generated one
+    fs_phred_fix *d_fixes = nullptr;        // Phred exceptions of the running call
+    int64_t d_fix_capacity = 0;
+    unsigned long long *d_n_fixes = nullptr;
 
     DeviceChunk chunk[kPipelineDepth];
     int64_t launches = 0, jit_launches = 0;
@@ -174,6 +187,8 @@ static void release_chunks(fs_engine *e) {
         cudaFree(c.pl);
         cudaFree(c.post);
         cudaFree(c.single);
+        cudaFree(c.post32);
+        cudaFree(c.single32);
         cudaFree(c.flags);
         cudaFree(c.gt);
         cudaFree(c.status);
@@ -206,6 +221,8 @@ void fs_destroy(fs_engine *e) {
         release_chunks(e);
         cudaFree(e->d_pl_table);
         cudaFree(e->d_fixups);
+        cudaFree(e->d_fixes);
+        cudaFree(e->d_n_fixes);
     }
     delete e;
 }
@@ -715,7 +732,8 @@ int fs_run_pl_device(fs_engine *e, int method, int64_t V, const uint16_t *d_pl, 
 
 // Device buffers of the host pipeline: `cap` variants per slot; lk (FP64 input, or the expansion of compact input for the
 // kernels that need it), pl and single only when this call uses them.
-static int ensure_chunks(fs_engine *e, int64_t cap, bool need_lk, bool need_pl, bool need_single) {
+static int ensure_chunks(fs_engine *e, int64_t cap, bool need_lk, bool need_pl, bool need_single, bool need_post32 = false,
+                         bool need_single32 = false) {
     const size_t S = (size_t)e->ped.s();
     for (DeviceChunk &c : e->chunk) {
         if (c.capacity < cap) {
@@ -725,6 +743,8 @@ static int ensure_chunks(fs_engine *e, int64_t cap, bool need_lk, bool need_pl, 
             cudaFree(c.pl);
             cudaFree(c.post);
             cudaFree(c.single);
+            cudaFree(c.post32);
+            cudaFree(c.single32);
             cudaFree(c.flags);
             cudaFree(c.gt);
             cudaFree(c.status);
@@ -746,6 +766,8 @@ static int ensure_chunks(fs_engine *e, int64_t cap, bool need_lk, bool need_pl, 
         if (need_lk && !c.lk) FS_CUDA(cudaMalloc(&c.lk, nd));
         if (need_single && !c.single) FS_CUDA(cudaMalloc(&c.single, nd));
         if (need_pl && !c.pl) FS_CUDA(cudaMalloc(&c.pl, std::max<size_t>((size_t)c.capacity * S * 3 * sizeof(uint16_t), 16)));
+        if (need_post32 && !c.post32) FS_CUDA(cudaMalloc(&c.post32, nd / 2));
+        if (need_single32 && !c.single32) FS_CUDA(cudaMalloc(&c.single32, nd / 2));
     }
     return FS_OK;
 }
@@ -764,8 +786,21 @@ static int run_host_one(fs_engine *e, int method, int64_t V, const BatchIo &io, 
     cap = std::max<int64_t>(1024, std::min<int64_t>(cap, 1 << 22)) & ~(int64_t)1023;
     cap = std::min<int64_t>(cap, (V + 1023) & ~(int64_t)1023);
     const bool fused = method == FS_METHOD_ES && e->is_nuclear && !e->force_generic_es; // kernel reads pl / skips single itself
-    int rc = ensure_chunks(e, cap, !io.pl || !fused, io.pl != nullptr, io.single != nullptr || !fused);
+    const bool want_single = io.single != nullptr || io.single_phred != nullptr;
+    int rc = ensure_chunks(e, cap, !io.pl || !fused, io.pl != nullptr, want_single || !fused, io.phred(), io.single_phred != nullptr);
     if (rc != FS_OK) return rc;
+    if (io.phred()) { // exception list of this call
+        const int64_t want = std::max<int64_t>(io.fix_capacity, 1);
+        if (e->d_fix_capacity < want) {
+            cudaFree(e->d_fixes);
+            e->d_fixes = nullptr;
+            e->d_fix_capacity = 0;
+            FS_CUDA(cudaMalloc(&e->d_fixes, (size_t)want * sizeof(fs_phred_fix)));
+            e->d_fix_capacity = want;
+        }
+        if (!e->d_n_fixes) FS_CUDA(cudaMalloc(&e->d_n_fixes, sizeof(unsigned long long)));
+        FS_CUDA(cudaMemset(e->d_n_fixes, 0, sizeof(unsigned long long)));
+    }
 
     e->last_kernel_ms = 0;
     auto drain = [&](DeviceChunk &c) -> int {
@@ -786,13 +821,27 @@ static int run_host_one(fs_engine *e, int method, int64_t V, const BatchIo &io, 
         else if (nd)
             FS_CUDA(cudaMemcpyAsync(c.lk, io.lk + (size_t)v0 * S * 3, nd, cudaMemcpyHostToDevice, c.stream));
         if (io.flags) FS_CUDA(cudaMemcpyAsync(c.flags, io.flags + v0, (size_t)nv, cudaMemcpyHostToDevice, c.stream));
-        BatchPtrs B{io.pl ? nullptr : c.lk, io.flags ? c.flags : nullptr, c.post, io.single ? c.single : nullptr, c.gt, c.status, nv};
+        BatchPtrs B{io.pl ? nullptr : c.lk, io.flags ? c.flags : nullptr, c.post, want_single ? c.single : nullptr, c.gt, c.status, nv};
         B.pl = io.pl ? c.pl : nullptr;
         FS_CUDA(cudaEventRecord(c.k0, c.stream));
         const int drc = dispatch(e, method, B, burn, rep, seed, v_offset + v0, c.stream, c.lk, c.single);
         if (drc != FS_OK) return drc;
+        if (nd && io.phred()) { // Phred codes instead of doubles: 4 bytes per value cross PCIe
+            const int64_t n3 = nv * (int64_t)S * 3, at = io.index_base + v0 * (int64_t)S * 3;
+            FS_CUDA(launch_phred_pack(c.post, c.post32, n3, at, e->d_fixes, io.fix_capacity, e->d_n_fixes, c.stream));
+            e->launches++;
+            if (io.single_phred) {
+                FS_CUDA(launch_phred_pack(c.single, c.single32, n3, at + FS_PHRED_FIX_SINGLE, e->d_fixes, io.fix_capacity, e->d_n_fixes, c.stream));
+                e->launches++;
+            }
+        }
         FS_CUDA(cudaEventRecord(c.k1, c.stream));
-        if (nd) {
+        if (nd && io.phred()) {
+            FS_CUDA(cudaMemcpyAsync(io.post_phred + (size_t)v0 * S * 3, c.post32, nd / 2, cudaMemcpyDeviceToHost, c.stream));
+            if (io.single_phred)
+                FS_CUDA(cudaMemcpyAsync(io.single_phred + (size_t)v0 * S * 3, c.single32, nd / 2, cudaMemcpyDeviceToHost, c.stream));
+            FS_CUDA(cudaMemcpyAsync(io.gt + (size_t)v0 * S, c.gt, (size_t)nv * S, cudaMemcpyDeviceToHost, c.stream));
+        } else if (nd) {
             FS_CUDA(cudaMemcpyAsync(io.post + (size_t)v0 * S * 3, c.post, nd, cudaMemcpyDeviceToHost, c.stream));
             if (io.single) FS_CUDA(cudaMemcpyAsync(io.single + (size_t)v0 * S * 3, c.single, nd, cudaMemcpyDeviceToHost, c.stream));
             FS_CUDA(cudaMemcpyAsync(io.gt + (size_t)v0 * S, c.gt, (size_t)nv * S, cudaMemcpyDeviceToHost, c.stream));
@@ -822,6 +871,13 @@ static int run_host_one(fs_engine *e, int method, int64_t V, const BatchIo &io, 
         const int drc = drain(c);
         if (drc != FS_OK && rc == FS_OK) rc = drc; // keep draining the other slots
     }
+    if (rc == FS_OK && io.phred()) { // the exceptions of the whole call
+        unsigned long long n = 0;
+        FS_CUDA(cudaMemcpy(&n, e->d_n_fixes, sizeof n, cudaMemcpyDeviceToHost));
+        const int64_t have = std::min<int64_t>((int64_t)n, io.fix_capacity);
+        if (have > 0) FS_CUDA(cudaMemcpy(io.fixes, e->d_fixes, (size_t)have * sizeof(fs_phred_fix), cudaMemcpyDeviceToHost));
+        if (io.n_fixes) *io.n_fixes = (int64_t)n;
+    }
     return rc;
 }
 
@@ -829,12 +885,17 @@ static int run_host_one(fs_engine *e, int method, int64_t V, const BatchIo &io, 
 static int run_host(fs_engine *e, int method, int64_t V, const BatchIo &io, int32_t burn, int32_t rep, uint64_t seed,
                     int64_t v_offset, const char *who) {
     if (!e) return fail(FS_E_ARG, std::string(who) + ": null engine");
-    if (V < 0 || (V > 0 && ((!io.lk && !io.pl) || !io.post || !io.gt || !io.status))) return fail(FS_E_ARG, std::string(who) + ": null buffer");
+    if (V < 0 || (V > 0 && ((!io.lk && !io.pl) || (!io.post && !io.post_phred) || !io.gt || !io.status)))
+        return fail(FS_E_ARG, std::string(who) + ": null buffer");
+    if (io.phred() && (io.fix_capacity < 0 || (io.fix_capacity > 0 && !io.fixes))) return fail(FS_E_ARG, std::string(who) + ": bad exception buffer");
+    if (io.n_fixes) *io.n_fixes = 0;
     if (e->parts.empty()) return run_host_one(e, method, V, io, burn, rep, seed, v_offset);
     const int G = (int)e->parts.size();
     const size_t S = (size_t)e->ped.s();
     std::vector<int> rcs(G, FS_OK);
     std::vector<std::string> errs(G);
+    std::vector<std::vector<fs_phred_fix>> part_fixes(io.phred() ? G : 0);
+    std::vector<int64_t> part_n(G, 0);
     auto work = [&](int g) {
         // slice boundaries on multiples of 1024 variants keep every GPU's tiles 16-byte aligned in the caller's buffers
         auto cut = [&](int k) { return k >= G ? V : std::min<int64_t>(V, (((V / G) * k) + 1023) & ~(int64_t)1023); };
@@ -844,8 +905,16 @@ static int run_host(fs_engine *e, int method, int64_t V, const BatchIo &io, int3
         if (io.lk) part.lk = io.lk + (size_t)a * S * 3;
         if (io.pl) part.pl = io.pl + (size_t)a * S * 3;
         if (io.flags) part.flags = io.flags + a;
-        part.post = io.post + (size_t)a * S * 3;
+        if (io.post) part.post = io.post + (size_t)a * S * 3;
         if (io.single) part.single = io.single + (size_t)a * S * 3;
+        if (io.phred()) {
+            part.post_phred = io.post_phred + (size_t)a * S * 3;
+            if (io.single_phred) part.single_phred = io.single_phred + (size_t)a * S * 3;
+            part_fixes[g].resize((size_t)io.fix_capacity);
+            part.fixes = part_fixes[g].data();
+            part.n_fixes = &part_n[g];
+            part.index_base = a * (int64_t)S * 3;
+        }
         part.gt = io.gt + (size_t)a * S;
         part.status = io.status + a;
         rcs[g] = run_host_one(e->parts[g], method, b - a, part, burn, rep, seed, v_offset + a);
@@ -859,6 +928,15 @@ static int run_host(fs_engine *e, int method, int64_t V, const BatchIo &io, int3
     for (int g = 0; g < G; g++) e->last_kernel_ms = std::max(e->last_kernel_ms, e->parts[g]->last_kernel_ms);
     for (int g = 0; g < G; g++)
         if (rcs[g] != FS_OK) return fail(rcs[g], "device " + std::to_string(e->parts[g]->device) + ": " + errs[g]);
+    if (io.phred()) { // the slices' exceptions, in slice order
+        int64_t total = 0, stored = 0;
+        for (int g = 0; g < G; g++) {
+            const int64_t have = std::min<int64_t>(part_n[g], io.fix_capacity);
+            for (int64_t k = 0; k < have && stored < io.fix_capacity; k++) io.fixes[stored++] = part_fixes[g][(size_t)k];
+            total += part_n[g];
+        }
+        if (io.n_fixes) *io.n_fixes = total;
+    }
     return FS_OK;
 }
 
@@ -874,6 +952,84 @@ int fs_run_pl(fs_engine *e, int method, int64_t V, const uint16_t *pl, const uin
     BatchIo io;
     io.pl = pl, io.flags = flags, io.post = post, io.single = single, io.gt = gt, io.status = status;
     return run_host(e, method, V, io, burn, rep, seed, v_offset, "fs_run_pl");
+}
+
+int fs_run_pl_phred(fs_engine *e, int method, int64_t V, const uint16_t *pl, const uint8_t *flags, int32_t burn, int32_t rep,
+                    uint64_t seed, int64_t v_offset, uint32_t *post_phred, uint32_t *single_phred, uint8_t *gt, uint8_t *status,
+                    fs_phred_fix *fixes, int64_t fix_capacity, int64_t *n_fixes) {
+    BatchIo io;
+    io.pl = pl, io.flags = flags, io.gt = gt, io.status = status;
+    io.post_phred = post_phred, io.single_phred = single_phred, io.fixes = fixes, io.fix_capacity = fix_capacity, io.n_fixes = n_fixes;
+    if (V > 0 && !post_phred) return fail(FS_E_ARG, "fs_run_pl_phred: null buffer");
+    return run_host(e, method, V, io, burn, rep, seed, v_offset, "fs_run_pl_phred");
+}
+
+int fs_phred_encode(fs_engine *e, int64_t n, const double *p, uint32_t *out, fs_phred_fix *fixes, int64_t fix_capacity, int64_t *n_fixes) {
+    if (!e) return fail(FS_E_ARG, "fs_phred_encode: null engine");
+    if (!e->parts.empty()) e = e->parts[0];
+    if (e->device < 0) return fail(FS_E_CUDA, "engine was created without a device (there is no CPU fallback)");
+    if (n < 0 || (n > 0 && (!p || !out)) || fix_capacity < 0 || (fix_capacity > 0 && !fixes)) return fail(FS_E_ARG, "fs_phred_encode: bad argument");
+    if (n_fixes) *n_fixes = 0;
+    if (n == 0) return FS_OK;
+    FS_CUDA(cudaSetDevice(e->device));
+    double *d_p = nullptr;
+    uint32_t *d_out = nullptr;
+    fs_phred_fix *d_fix = nullptr;
+    unsigned long long *d_n = nullptr, count = 0;
+    auto release = [&]() {
+        cudaFree(d_p);
+        cudaFree(d_out);
+        cudaFree(d_fix);
+        cudaFree(d_n);
+    };
+    cudaError_t rc = cudaMalloc(&d_p, (size_t)n * sizeof(double));
+    if (rc == cudaSuccess) rc = cudaMalloc(&d_out, (size_t)n * sizeof(uint32_t));
+    if (rc == cudaSuccess) rc = cudaMalloc(&d_fix, (size_t)std::max<int64_t>(fix_capacity, 1) * sizeof(fs_phred_fix));
+    if (rc == cudaSuccess) rc = cudaMalloc(&d_n, sizeof count);
+    if (rc == cudaSuccess) rc = cudaMemset(d_n, 0, sizeof count);
+    if (rc == cudaSuccess) rc = cudaMemcpy(d_p, p, (size_t)n * sizeof(double), cudaMemcpyHostToDevice);
+    if (rc == cudaSuccess) rc = launch_phred_pack(d_p, d_out, n, 0, d_fix, fix_capacity, d_n, nullptr);
+    if (rc == cudaSuccess) rc = cudaMemcpy(out, d_out, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+    if (rc == cudaSuccess) rc = cudaMemcpy(&count, d_n, sizeof count, cudaMemcpyDeviceToHost);
+    const int64_t have = std::min<int64_t>((int64_t)count, fix_capacity);
+    if (rc == cudaSuccess && have > 0) rc = cudaMemcpy(fixes, d_fix, (size_t)have * sizeof(fs_phred_fix), cudaMemcpyDeviceToHost);
+    release();
+    if (rc != cudaSuccess) return cuda_fail(rc, "fs_phred_encode");
+    e->launches++;
+    if (n_fixes) *n_fixes = (int64_t)count;
+    return FS_OK;
+}
+
+int fs_phred_text(uint32_t code, char *buf) {
+    if (!buf) return -1;
+    const uint32_t kind = code & (3u << 30);
+    int n = 0;
+    if (kind == FS_PHRED_FIX) {
+        buf[0] = 0;
+        return -1;
+    }
+    if (kind == FS_PHRED_ZERO) {
+        buf[n++] = '0';
+    } else if (kind == FS_PHRED_INF) {
+        std::memcpy(buf, "99999", 5);
+        n = 5;
+    } else {
+        n = famseq::emit_decimal6(buf, code & 0xfffffu, (int)((code >> 20) & 63u) - 32);
+    }
+    buf[n] = 0;
+    return n;
+}
+
+int fs_phred_text_exact(double p, char *buf) { // file.cpp:702-749: -10*log10(p); +inf prints 99999, anything else its absolute value
+    if (!buf) return -1;
+    const double v = -10 * std::log10(p);
+    std::string s;
+    if (v == std::numeric_limits<double>::infinity())
+        s = "99999";
+    else
+        famseq::append_g(s, std::fabs(v));
+    std::memcpy(buf, s.c_str(), s.size() + 1);
+    return (int)s.size();
 }
 
 } // extern "C"

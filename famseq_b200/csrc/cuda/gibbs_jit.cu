@@ -7,23 +7,29 @@
 // founder cases are resolved at generation time, a genotype is kept as the byte offset of its table row (g * 128), a
 // transmission look-up is one integer multiply-add and three LDS.64 with immediate offsets.
 //
-// Round 2: CACHED FULL CONDITIONALS.  A member's three conditional weights depend on the current genotypes of its
-// parents, children and spouses only.  On sequencing data most chains sit in one state nearly all the time (a Gibbs step
-// changes the member's genotype in 8e-5 of the steps of the benchmark pedigrees, 2e-2 on TestData/loftest with 8 of 11
-// members unsequenced), so recomputing the weights in every step -- what the reference does, and what round 1's kernel
-// did at ~50 instructions, 23 of them FP64, and 14-17 shared-memory wavefronts per step -- is almost always redundant.
-// Every chain now keeps, per member, the normalised weights of the last evaluation (P0 and Q2 = 1 - P2 in registers or
-// thread-private shared-memory columns) and a dirty bit; a step is
-//        if (dirty) { close the run of the old weights; recompute; store; }        // rare, divergent
-//        draw: g = rd < P0 ? 0 : rd > Q2 ? 2 : 1;                                 // the reference's rule, family.cpp:2161-2173
-//        if (g changed) dirty |= {parents, children, spouses of the member};       // constant masks
-// ~33 instructions, 3 of them FP64, at most two LDS.  The draws are exactly the ones a recomputation would give: same
-// inputs, same instruction sequence, same weights.  Rao-Blackwellisation (family.cpp:2175-2178) adds the SAME normalised
-// weights once per sampling sweep for as long as they stay valid; the kernel adds n * P when the run of n sampling
-// sweeps ends instead of n times P (one rounding per run instead of n: differs from sweep-by-sweep accumulation by a few
-// ulps, far inside the 1e-9 parity tolerance; tests compare the two kernels to 1e-12 relative).
-// Accumulators, P1, P2 and the sweep index of the last evaluation live in a block-private scratch that stays in L2 and is
-// touched only when a run ends.
+// Round 2: CACHED FULL CONDITIONALS, INTEGER DRAWS, SPECULATIVE GROUPS.
+// A member's three conditional weights depend on the current genotypes of its parents, children and spouses only.  On
+// sequencing data most chains sit in one state nearly all the time (a Gibbs step changes the member's genotype in 8e-5 of
+// the steps of the benchmark pedigrees), so recomputing the weights in every step -- what the reference does, and what
+// round 1's kernel did at ~50 instructions, 23 of them FP64, and 14-17 shared-memory wavefronts per step -- is almost
+// always redundant.  Every chain keeps, per member, the outcome of the last evaluation and a dirty bit:
+//   * the draw rule rd < P0 -> 0, rd > 1 - P2 -> 2 (family.cpp:2161-2173) with rd = (u + 0.5) 2^-31, u the top 31 bits of
+//     the member's Philox word, is EXACTLY u < T0 -> 0, u >= T2 -> 2 for the integers T0 = ceil(P0 2^31 - 1/2),
+//     T2 = floor((1 - P2) 2^31 - 1/2) + 1 in [0, 2^31]; the two thresholds (two 32-bit registers per member) are all a
+//     draw needs, and a draw is four integer instructions -- no FP64, no shared memory;
+//   * members are taken in groups of eight.  If no member of the group is dirty, the eight draws are made side by side
+//     from the cached thresholds (independent instructions: this is where the kernel gets its instruction-level
+//     parallelism back); if then none of the changed members has a neighbour inside the group, the group commits:
+//     genotypes replaced, neighbours of changed members marked dirty (constant masks).  Otherwise -- a dirty member, or a
+//     change next to a group mate; about one group in ten per warp on the benchmark data -- the group is redone member by
+//     member in the reference's order: evaluate if dirty (an out-of-line function per member: close the run of the old
+//     weights, recompute, store), draw, mark.  The random words are the same on both paths, so the chain is the one the
+//     sweep-by-sweep sampler produces with this stream.
+//   * Rao-Blackwellisation (family.cpp:2175-2178) adds the SAME normalised weights once per sampling sweep for as long as
+//     they stay valid; the kernel adds n * P when the run of n sampling sweeps ends instead of n times P (one rounding per
+//     run instead of n: differs from sweep-by-sweep accumulation by ~1e-14 relative, far inside the 1e-9 parity
+//     tolerance; tests compare the two kernels to 1e-12).  Accumulators, P0..P2 and the sweep index of the last
+//     evaluation live in a block-private scratch that stays in L2 and is touched only when a run ends.
 // The kernel carries the sweep twice, with the autosomal and with the chrX rules (a thread takes the loop of its
 // variant).  The straight-line code covers what a sweep almost always is: weight sums that are positive normal
 // numbers.  Chains in which a sum leaves that range are marked (status 2) and redone by the table-driven kernel,
@@ -142,9 +148,9 @@ std::vector<Member> decode(const McmcPlan &pl) {
     return m;
 }
 
-// Where the cached weights (P0, Q2 = 1 - P2) of every member live: the first n_p_reg members in registers, the others in
-// thread-private shared-memory columns.  Per member, six rows of the block-private global scratch hold the three
-// accumulators, P1, P2 and the sweep index of the last evaluation.
+// Where the cached draw thresholds (T0, T2: two 32-bit words) of every member live: the first n_p_reg members in registers,
+// the others in thread-private shared-memory columns.  Per member, seven rows of the block-private global scratch hold the
+// three accumulators, P0, P1, P2 and the sweep index of the last evaluation.
 struct Layout {
     int n = 0, n_reg = 0, smem_pairs = 0;
     std::vector<int> pair; // shared-memory pair index of the member, -1 = registers
@@ -159,13 +165,14 @@ Layout make_layout(int n, const GibbsJitConfig &cfg) {
     return L;
 }
 
-constexpr int kScratchRows = 6; // A0 A1 A2 P1 P2 LAST
-size_t smem_bytes(const Layout &L, int tb) { return (size_t)kTabBytes + (size_t)L.smem_pairs * 2 * tb * 8; }
+constexpr int kScratchRows = 7; // A0 A1 A2 P0 P1 P2 LAST
+constexpr int kGroup = 8;       // members drawn side by side; divides 32, so a group lies within one word of the dirty mask
+size_t smem_bytes(const Layout &L, int tb) { return (size_t)kTabBytes + (size_t)L.smem_pairs * 2 * tb * 4; }
 
-std::string p0_ref(const Layout &L, int i) { return L.pair[i] < 0 ? "P" + std::to_string(i) : "sa[" + std::to_string(L.pair[i] * 2) + " * TB]"; }
-std::string q2_ref(const Layout &L, int i) { return L.pair[i] < 0 ? "Q" + std::to_string(i) : "sa[" + std::to_string(L.pair[i] * 2 + 1) + " * TB]"; }
+std::string t0_ref(const Layout &L, int i) { return L.pair[i] < 0 ? "T" + std::to_string(i) : "st[" + std::to_string(L.pair[i] * 2) + " * TB]"; }
+std::string t2_ref(const Layout &L, int i) { return L.pair[i] < 0 ? "U" + std::to_string(i) : "st[" + std::to_string(L.pair[i] * 2 + 1) + " * TB]"; }
 std::string scratch_ref(int i, int k) { return "wg + " + std::to_string(i * kScratchRows + k) + " * TB"; }
-enum { ROW_A0 = 0, ROW_P1 = 3, ROW_P2 = 4, ROW_LAST = 5 };
+enum { ROW_A0 = 0, ROW_P0 = 3, ROW_P1 = 4, ROW_P2 = 5, ROW_LAST = 6 };
 
 // Members whose weights depend on the genotype of member j: its parents (j is one of their children), its children (their
 // own transmission) and its spouses (co-parents of its children).  The chrX sweep skips the children factor of females,
@@ -188,26 +195,42 @@ std::vector<std::vector<int>> neighbours(const std::vector<Member> &M) {
 
 const char *table_of(bool chrx, bool male) { return chrx ? (male ? "tXM" : "tXF") : "tA"; }
 
-// One Gibbs step of member i (family.cpp:2113-2178 / :2195-2295).
+// Members whose current genotype the evaluation of member i reads (generation-time constant).
+std::vector<int> inputs_of(const std::vector<Member> &M, int i, bool chrx) {
+    std::vector<int> in;
+    auto add = [&](int k) {
+        if (std::find(in.begin(), in.end(), k) == in.end()) in.push_back(k);
+    };
+    const Member &m = M[i];
+    if (!m.founder) add(m.mother), add(m.father);
+    if (!(chrx && !m.male))
+        for (const Member::Link &l : m.links) add(l.child), add(l.other);
+    std::sort(in.begin(), in.end());
+    return in;
+}
+
+std::string eval_name(int i, bool chrx) { return std::string(chrx ? "eval_x_" : "eval_a_") + std::to_string(i); }
+
+// The evaluation of member i's full conditional (family.cpp:2113-2178 / :2195-2295) as a function of its own, kept out of
+// line (the sweep loop then holds only draws and call sites): closes the run of the old weights, forms the three weights
+// from the member's likelihood and its parents', children's and spouses' current genotypes, normalises them, stores them
+// and returns the draw thresholds.
 // chrX sweeps (family.cpp:2183-2297): a member's own transmission comes from the table of its sex, a child's from the
 // table of the child's sex, and only males get the children factor.
-void emit_member(std::ostringstream &o, const std::vector<Member> &M, const Layout &L, const std::vector<std::vector<int>> &nb, int i, bool chrx) {
+void emit_evaluation_function(std::ostringstream &o, const std::vector<Member> &M, int i, bool chrx) {
     const Member &m = M[i];
-    const int n = (int)M.size(), words = (n + 31) / 32;
-    const std::string dw = "D" + std::to_string(i / 32), bit = std::to_string(1u << (i % 32)) + "u";
-    const std::string P0 = p0_ref(L, i), Q2 = q2_ref(L, i);
-    o << "            // member " << i << (m.founder ? " (founder" : " (child of ");
-    if (!m.founder) o << m.mother << " x " << m.father;
-    o << (m.male ? ", male)\n" : ", not male)\n");
-    o << "            if (" << dw << " & " << bit << ") { // a neighbour changed since the weights were evaluated\n";
-    o << "                " << dw << " &= ~" << bit << ";\n";
-    // close the run of the old weights: they were valid in sweeps LAST .. sweep-1, of which n are sampling sweeps
-    o << "                { const double run = fmax(0.0, __dsub_rn(tD, fmax(__ldcg(" << scratch_ref(i, ROW_LAST) << "), first)));\n"
-      << "                  *(" << scratch_ref(i, ROW_A0) << ") = __dadd_rn(__ldcg(" << scratch_ref(i, ROW_A0) << "), __dmul_rn(run, " << P0 << "));\n"
-      << "                  *(" << scratch_ref(i, ROW_A0 + 1) << ") = __dadd_rn(__ldcg(" << scratch_ref(i, ROW_A0 + 1) << "), __dmul_rn(run, __ldcg("
-      << scratch_ref(i, ROW_P1) << ")));\n"
-      << "                  *(" << scratch_ref(i, ROW_A0 + 2) << ") = __dadd_rn(__ldcg(" << scratch_ref(i, ROW_A0 + 2) << "), __dmul_rn(run, __ldcg("
-      << scratch_ref(i, ROW_P2) << "))); }\n";
+    const char *ind = "    ";
+    o << "__device__ __noinline__ Rc " << eval_name(i, chrx) << "(const double *__restrict__ lkv, double *wg, double tD, double first, u32 tA, u32 tXF, u32 tXM, "
+      << "u32 worst";
+    if (m.founder) o << ", double " << (m.male ? "pm0, double pm1, double pm2" : "pa0, double pa1, double pa2");
+    for (int k : inputs_of(M, i, chrx)) o << ", u32 o" << k;
+    o << ") {\n    (void)tA; (void)tXF; (void)tXM;\n";
+    // close the run of the old weights: they were valid in sweeps LAST .. sweep-1, of which `run` are sampling sweeps
+    o << ind << "{ const double run = fmax(0.0, __dsub_rn(tD, fmax(__ldcg(" << scratch_ref(i, ROW_LAST) << "), first)));\n";
+    for (int g = 0; g < 3; g++)
+        o << ind << "  *(" << scratch_ref(i, ROW_A0 + g) << ") = __dadd_rn(__ldcg(" << scratch_ref(i, ROW_A0 + g) << "), __dmul_rn(run, __ldcg("
+          << scratch_ref(i, ROW_P0 + g) << ")));\n";
+    o << ind << "}\n";
     // own factor (1e6 * prior) * lk for founders, 1e6 * lk otherwise (family.cpp:2115-2126)
     for (int g = 0; g < 3; g++) {
         std::ostringstream lkx, base;
@@ -219,51 +242,116 @@ void emit_member(std::ostringstream &o, const std::vector<Member> &M, const Layo
             base << "__dmul_rn(1000000.0, " << (m.male ? "pm" : "pa") << g << ")";
         else
             base << "1000000.0";
-        o << "                double w" << g << " = __dmul_rn(" << base.str() << ", " << lkx.str() << ");\n";
+        o << ind << "double w" << g << " = __dmul_rn(" << base.str() << ", " << lkx.str() << ");\n";
     }
     if (!m.founder) // transmission from the parents' current genotypes: entry g*9 + mother*3 + father
-        o << "                { const u32 ta = " << table_of(chrx, m.male) << " + o" << m.mother << " * 3u + o" << m.father << ";\n"
-          << "                  w0 = __dmul_rn(w0, lds64(ta)); w1 = __dmul_rn(w1, lds64(ta + " << 9 * kRow << ")); w2 = __dmul_rn(w2, lds64(ta + "
+        o << ind << "{ const u32 ta = " << table_of(chrx, m.male) << " + o" << m.mother << " * 3u + o" << m.father << ";\n"
+          << ind << "  w0 = __dmul_rn(w0, lds64(ta)); w1 = __dmul_rn(w1, lds64(ta + " << 9 * kRow << ")); w2 = __dmul_rn(w2, lds64(ta + "
           << 18 * kRow << ")); }\n";
     for (const Member::Link &l : m.links) {
         if (chrx && !m.male) break; // family.cpp:2230-2257
         const char *tA = table_of(chrx, l.child_male);
         if (m.male) // this member is the father: entry child*9 + mother*3 + g
-            o << "                { const u32 ta = " << tA << " + o" << l.child << " * 9u + o" << l.other << " * 3u;\n"
-              << "                  w0 = __dmul_rn(w0, lds64(ta)); w1 = __dmul_rn(w1, lds64(ta + " << kRow
-              << ")); w2 = __dmul_rn(w2, lds64(ta + " << 2 * kRow << ")); }\n";
+            o << ind << "{ const u32 ta = " << tA << " + o" << l.child << " * 9u + o" << l.other << " * 3u;\n"
+              << ind << "  w0 = __dmul_rn(w0, lds64(ta)); w1 = __dmul_rn(w1, lds64(ta + " << kRow << ")); w2 = __dmul_rn(w2, lds64(ta + " << 2 * kRow
+              << ")); }\n";
         else // this member is the mother: entry child*9 + g*3 + father
-            o << "                { const u32 ta = " << tA << " + o" << l.child << " * 9u + o" << l.other << ";\n"
-              << "                  w0 = __dmul_rn(w0, lds64(ta)); w1 = __dmul_rn(w1, lds64(ta + " << 3 * kRow
-              << ")); w2 = __dmul_rn(w2, lds64(ta + " << 6 * kRow << ")); }\n";
+            o << ind << "{ const u32 ta = " << tA << " + o" << l.child << " * 9u + o" << l.other << ";\n"
+              << ind << "  w0 = __dmul_rn(w0, lds64(ta)); w1 = __dmul_rn(w1, lds64(ta + " << 3 * kRow << ")); w2 = __dmul_rn(w2, lds64(ta + " << 6 * kRow
+              << ")); }\n";
     }
-    o << "                const double sum = __dadd_rn(__dadd_rn(w0, w1), w2);\n";
+    o << ind << "const double sum = __dadd_rn(__dadd_rn(w0, w1), w2);\n";
     // The straight-line code assumes a positive normal sum with exponent in [-963, 963) (no sign test, Newton reciprocal);
     // `worst` records whether that ever failed, in which case the chain is redone by the table-driven kernel.
-    o << "                worst = max(worst, (u32)__double2hiint(sum) - 0x03c00000u);\n";
-    o << "                const double inv = newton_reciprocal(sum);\n";
-    o << "                const double p0 = __dmul_rn(w0, inv), p1 = __dmul_rn(w1, inv), p2 = __dmul_rn(w2, inv);\n";
-    o << "                " << P0 << " = p0; " << Q2 << " = __dsub_rn(1.0, p2);\n";
-    o << "                *(" << scratch_ref(i, ROW_P1) << ") = p1; *(" << scratch_ref(i, ROW_P2) << ") = p2; *(" << scratch_ref(i, ROW_LAST) << ") = tD;\n";
-    o << "            }\n";
-    // the draw (family.cpp:2161-2173): rd < w0 -> 0, rd > 1 - w2 -> 2, else 1, on the normalised weights
-    o << "            {\n";
-    if ((i & 3) == 0) o << "                philox((u32)sweep, " << (i >> 2) << "u, gv_lo, gv_hi, k0, k1, r0, r1, r2, r3);\n";
-    // (u + 0.5) * 2^-32 without an int-to-double conversion: 1 + u * 2^-32 assembled from bits, then one exact subtraction
-    o << "                const double rd = __dsub_rn(__hiloint2double((int)(0x3ff00000u | (r" << (i & 3) << " >> 12)), (int)(r" << (i & 3)
-      << " << 20)), 0x1.ffffffffp-1);\n";
-    o << "                const u32 g = (rd < " << P0 << ") ? 0u : ((rd > " << Q2 << ") ? " << 2 * kRow << "u : " << kRow << "u);\n";
-    std::vector<unsigned> mask(words, 0u);
-    for (int j : nb[i]) mask[j / 32] |= 1u << (j % 32);
-    o << "                const u32 changed = (g != o" << i << ") ? 0xffffffffu : 0u;\n";
-    for (int w = 0; w < words; w++)
-        if (mask[w]) o << "                D" << w << " |= changed & " << mask[w] << "u;\n";
-    o << "                o" << i << " = g;\n";
-    o << "            }\n";
+    o << ind << "worst = max(worst, (u32)__double2hiint(sum) - 0x03c00000u);\n";
+    o << ind << "const double inv = newton_reciprocal(sum);\n";
+    o << ind << "const double p0 = __dmul_rn(w0, inv), p1 = __dmul_rn(w1, inv), p2 = __dmul_rn(w2, inv);\n";
+    o << ind << "*(" << scratch_ref(i, ROW_P0) << ") = p0; *(" << scratch_ref(i, ROW_P1) << ") = p1; *(" << scratch_ref(i, ROW_P2) << ") = p2; *("
+      << scratch_ref(i, ROW_LAST) << ") = tD;\n";
+    // rd < p0  <=>  u < ceil(p0 2^31 - 1/2);   rd > 1 - p2  <=>  u >= floor((1 - p2) 2^31 - 1/2) + 1     (rd = (u + 1/2) 2^-31, exact)
+    o << ind << "Rc r;\n"
+      << ind << "r.t0 = __double2uint_ru(__fma_rn(p0, 2147483648.0, -0.5));\n"
+      << ind << "r.t2 = (u32)(__double2int_rd(__fma_rn(__dsub_rn(1.0, p2), 2147483648.0, -0.5)) + 1);\n"
+      << ind << "r.worst = worst;\n"
+      << ind << "return r;\n}\n";
 }
 
+std::vector<unsigned> neighbour_mask(const std::vector<std::vector<int>> &nb, int i, int words) {
+    std::vector<unsigned> mask(words, 0u);
+    for (int j : nb[i]) mask[j / 32] |= 1u << (j % 32);
+    return mask;
+}
+
+// One member the reference's way: evaluate if a neighbour changed, draw, mark the neighbours if the genotype changed.
+void emit_member_serial(std::ostringstream &o, const std::vector<Member> &M, const Layout &L, const std::vector<std::vector<int>> &nb, int i, bool chrx,
+                        const std::string &u) {
+    const Member &m = M[i];
+    const int n = (int)M.size(), words = (n + 31) / 32;
+    const std::string dw = "D" + std::to_string(i / 32), bit = std::to_string(1u << (i % 32)) + "u";
+    o << "                if (" << dw << " & " << bit << ") { // member " << i << ": a neighbour changed since its weights were evaluated\n"
+      << "                    " << dw << " &= ~" << bit << ";\n"
+      << "                    const Rc r = " << eval_name(i, chrx) << "(lkv, wg, tD, first, tA, tXF, tXM, worst";
+    if (m.founder) o << (m.male ? ", pm0, pm1, pm2" : ", pa0, pa1, pa2");
+    for (int k : inputs_of(M, i, chrx)) o << ", o" << k;
+    o << ");\n                    " << t0_ref(L, i) << " = r.t0; " << t2_ref(L, i) << " = r.t2; worst = r.worst;\n                }\n";
+    o << "                { const u32 g = (" << u << " < " << t0_ref(L, i) << ") ? 0u : ((" << u << " >= " << t2_ref(L, i) << ") ? " << 2 * kRow << "u : " << kRow
+      << "u);\n                  const u32 changed = (g != o" << i << ") ? 0xffffffffu : 0u;\n";
+    const std::vector<unsigned> mask = neighbour_mask(nb, i, words);
+    for (int w = 0; w < words; w++)
+        if (mask[w]) o << "                  D" << w << " |= changed & " << mask[w] << "u;\n";
+    o << "                  o" << i << " = g; }\n";
+}
+
+// One sweep: groups of kGroup members, each drawn side by side when it can be, member by member when it must be.
 void emit_sweep(std::ostringstream &o, const std::vector<Member> &M, const Layout &L, const std::vector<std::vector<int>> &nb, bool chrx) {
-    for (int i = 0; i < (int)M.size(); i++) emit_member(o, M, L, nb, i, chrx);
+    const int n = (int)M.size(), words = (n + 31) / 32;
+    for (int a = 0; a < n; a += kGroup) {
+        const int b = std::min(n, a + kGroup), w = a / 32;
+        unsigned gmask = 0;
+        for (int i = a; i < b; i++) gmask |= 1u << (i % 32);
+        o << "            { // members " << a << " .. " << b - 1 << "\n";
+        // the random words of the group (word i%4 of Philox block i/4), kept in their own variables so that both paths read the same
+        for (int i = a; i < b; i++)
+            if ((i & 3) == 0 || i == a) {
+                const int blk = i >> 2;
+                o << "                u32 x" << blk << "_0, x" << blk << "_1, x" << blk << "_2, x" << blk << "_3;\n"
+                  << "                philox((u32)sweep, " << blk << "u, gv_lo, gv_hi, k0, k1, x" << blk << "_0, x" << blk << "_1, x" << blk << "_2, x" << blk
+                  << "_3);\n";
+            }
+        auto u_of = [](int i) { return "(x" + std::to_string(i >> 2) + "_" + std::to_string(i & 3) + " >> 1)"; };
+        o << "                bool done = false;\n"
+          << "                if (__builtin_expect((D" << w << " & " << gmask << "u) == 0u, 1)) { // nobody dirty: draw the group side by side\n";
+        for (int i = a; i < b; i++)
+            o << "                    const u32 g" << i << " = (" << u_of(i) << " < " << t0_ref(L, i) << ") ? 0u : ((" << u_of(i) << " >= " << t2_ref(L, i) << ") ? "
+              << 2 * kRow << "u : " << kRow << "u);\n";
+        for (int ww = 0; ww < words; ww++) {
+            bool any = false;
+            for (int i = a; i < b; i++) any = any || neighbour_mask(nb, i, words)[ww];
+            if (!any) continue;
+            o << "                    const u32 n" << ww << " = 0u";
+            for (int i = a; i < b; i++) {
+                const unsigned mk = neighbour_mask(nb, i, words)[ww];
+                if (mk) o << " | ((g" << i << " != o" << i << ") ? " << mk << "u : 0u)";
+            }
+            o << ";\n";
+        }
+        bool own_word = false;
+        for (int i = a; i < b; i++) own_word = own_word || neighbour_mask(nb, i, words)[w];
+        if (own_word)
+            o << "                    if (__builtin_expect((n" << w << " & " << gmask << "u) == 0u, 1)) { // no change next to a group mate: commit\n";
+        else
+            o << "                    {\n";
+        for (int i = a; i < b; i++) o << "                        o" << i << " = g" << i << ";\n";
+        for (int ww = 0; ww < words; ww++) {
+            bool any = false;
+            for (int i = a; i < b; i++) any = any || neighbour_mask(nb, i, words)[ww];
+            if (any) o << "                        D" << ww << " |= n" << ww << ";\n";
+        }
+        o << "                        done = true;\n                    }\n                }\n"
+          << "                if (__builtin_expect(!done, 0)) { // member by member, in the reference's order\n";
+        for (int i = a; i < b; i++) emit_member_serial(o, M, L, nb, i, chrx, u_of(i));
+        o << "                }\n            }\n";
+    }
 }
 
 } // namespace
@@ -271,16 +359,15 @@ void emit_sweep(std::ostringstream &o, const std::vector<Member> &M, const Layou
 GibbsJitConfig gibbs_jit_default_config(const McmcParams &P) {
     const int n = P.plan.n;
     GibbsJitConfig c;
-    // Two warps per SM sub-partition: 256 chains per SM, up to 255 registers each.  A chain needs ~70 registers for the step
-    // itself, one per member for the genotypes and four per member whose cached weights (P0, Q2) sit in registers; the
-    // other members' pairs go to thread-private shared-memory columns (16 bytes per member and chain).  When even that does
-    // not fit (very large pedigrees) the block shrinks.
-    c.tb = 256;
+    // A chain needs ~60 registers for the step itself, one per member for the genotypes and two per member whose draw
+    // thresholds sit in registers; the other members' pairs go to thread-private shared-memory columns (8 bytes per member
+    // and chain).  The block is as large as the register file allows (the step is a chain of short integer dependencies:
+    // warps hide it), in multiples of 128 threads.
     c.blocks = 1;
-    c.n_p_reg = std::max(0, std::min(n, (250 - (84 + n)) / 4));
-    while (c.tb > 32 && kTabBytes + (size_t)(n - c.n_p_reg) * 16 * c.tb > kSmemPerBlockMax) c.tb -= 32;
-    if (c.n_p_reg == n) // small pedigree, everything in registers: more than one block per SM
-        c.blocks = std::max(1, std::min(4, 65536 / (c.tb * (80 + 5 * n))));
+    c.n_p_reg = std::max(0, std::min(n, (250 - (64 + n)) / 2));
+    const int regs = 64 + n + 2 * c.n_p_reg;
+    c.tb = regs <= 124 ? 512 : (regs <= 164 ? 384 : 256);
+    while (c.tb > 32 && kTabBytes + (size_t)(n - c.n_p_reg) * 8 * c.tb > kSmemPerBlockMax) c.tb -= 32;
     c.tb = env_int("FAMSEQ_JIT_TB", c.tb);
     c.blocks = std::max(1, env_int("FAMSEQ_JIT_BLOCKS", c.blocks));
     c.n_p_reg = std::min(n, std::max(0, env_int("FAMSEQ_JIT_PREG", c.n_p_reg)));
@@ -295,8 +382,8 @@ std::string gibbs_jit_source(const McmcParams &P, const GibbsJitConfig &cfg) {
     const std::vector<std::vector<int>> nb = neighbours(M);
     std::ostringstream o;
     o << "// generated by famseq_b200 (gibbs_jit.cu) for one pedigree: " << n << " members, " << S << " input columns\n";
-    o << "// layout: " << cfg.tb << " chains per block; cached weights of " << L.n_reg << " members in registers, of " << L.smem_pairs
-      << " in shared memory; accumulators and run bookkeeping in a block-private L2 scratch\n";
+    o << "// layout: " << cfg.tb << " chains per block; draw thresholds of " << L.n_reg << " members in registers, of " << L.smem_pairs
+      << " in shared memory; weights, accumulators and run bookkeeping in a block-private L2 scratch\n";
     o << "#define TB " << cfg.tb << "\n#define NCOL " << S << "\n";
     o << kPrelude;
     o << "__constant__ u64 TAB_BITS[81] = {";
@@ -310,23 +397,26 @@ std::string gibbs_jit_source(const McmcParams &P, const GibbsJitConfig &cfg) {
     o << "0};\n";
     const unsigned unseq = (C.unseq_fail[0] ? 1u : 0u) | (C.unseq_fail[1] ? 2u : 0u) | (C.unseq_fail[2] ? 4u : 0u) | (C.unseq_fail[3] ? 8u : 0u);
 
+    o << "\nstruct Rc { u32 t0, t2, worst; };\n";
+    for (int x = 0; x < 2; x++)
+        for (int i = 0; i < n; i++) emit_evaluation_function(o, M, i, x == 1);
     o << "\nextern \"C\" __global__ void __launch_bounds__(TB, " << cfg.blocks << ")\n"
       << "famseq_gibbs(const double *__restrict__ lk, const u8 *__restrict__ flags, double *__restrict__ post,\n"
       << "             double *__restrict__ single, u8 *__restrict__ gt, u8 *__restrict__ status, i64 V, int burn, int rep,\n"
       << "             u64 seed, i64 v_offset, double *scratch, int n_tiles) {\n"
       << "    extern __shared__ __align__(16) unsigned char smem_raw[];\n"
       << "    double *s_tab = (double *)smem_raw;              // [81][" << kCopies << "]\n"
-      << "    double *s_vec = s_tab + 81 * " << kCopies << ";           // [" << L.smem_pairs << " * 2][TB] thread-private columns: P0, Q2\n"
+      << "    u32 *s_thr = (u32 *)(s_tab + 81 * " << kCopies << ");    // [" << L.smem_pairs << " * 2][TB] thread-private columns: T0, T2\n"
       << "    const int tid = threadIdx.x, lane = tid & 31;\n"
       << "    for (int e = tid; e < 81 * " << kCopies << "; e += TB) s_tab[e] = __longlong_as_double((i64)TAB_BITS[e / " << kCopies << "]);\n"
       << "    __syncthreads();\n"
       << "    u32 tab_addr = (u32)__cvta_generic_to_shared(s_tab) + (u32)(lane & " << (kCopies - 1) << ") * 8u;\n"
       << "    asm volatile(\"\" : \"+r\"(tab_addr) :: \"memory\"); // table reads stay below the barrier\n"
-      << "    double *sa = s_vec + tid;\n"
-      << "    double *wg = scratch + (size_t)blockIdx.x * " << n * kScratchRows << " * TB + tid; // [member][A0 A1 A2 P1 P2 LAST][TB], block-private\n"
+      << "    u32 *st = s_thr + tid;\n"
+      << "    double *wg = scratch + (size_t)blockIdx.x * " << n * kScratchRows << " * TB + tid; // [member][A0 A1 A2 P0 P1 P2 LAST][TB], block-private\n"
       << "    const u32 k0 = (u32)seed, k1 = (u32)(seed >> 32);\n"
       << "    const double lrc = __longlong_as_double((i64)" << bits(C.lrc) << ");\n"
-      << "    (void)sa; (void)wg;\n\n"
+      << "    (void)st; (void)wg;\n\n"
       << "    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {\n"
       << "        const i64 v = (i64)tile * TB + tid;\n"
       << "        if (v >= V) continue;\n"
@@ -376,9 +466,9 @@ std::string gibbs_jit_source(const McmcParams &P, const GibbsJitConfig &cfg) {
       << "        // chain state: nothing evaluated yet (every member dirty), empty runs\n";
     for (int i = 0; i < n; i++) {
         if (L.pair[i] < 0)
-            o << "        double P" << i << " = 0.0, Q" << i << " = 0.0;\n";
+            o << "        u32 T" << i << " = 0u, U" << i << " = 0u;\n";
         else
-            o << "        " << p0_ref(L, i) << " = 0.0; " << q2_ref(L, i) << " = 0.0;\n";
+            o << "        " << t0_ref(L, i) << " = 0u; " << t2_ref(L, i) << " = 0u;\n";
         for (int k = 0; k < kScratchRows; k++) o << "        *(" << scratch_ref(i, k) << ") = 0.0;\n";
     }
     for (int w = 0; w < words; w++) {
@@ -412,7 +502,8 @@ std::string gibbs_jit_source(const McmcParams &P, const GibbsJitConfig &cfg) {
     for (int i = 0; i < n; i++) {
         o << "        {\n"
           << "            const double run = fmax(0.0, __dsub_rn(tD, fmax(__ldcg(" << scratch_ref(i, ROW_LAST) << "), first)));\n"
-          << "            const double p0 = __ddiv_rn(__dadd_rn(__ldcg(" << scratch_ref(i, ROW_A0) << "), __dmul_rn(run, " << p0_ref(L, i) << ")), nrep);\n"
+          << "            const double p0 = __ddiv_rn(__dadd_rn(__ldcg(" << scratch_ref(i, ROW_A0) << "), __dmul_rn(run, __ldcg(" << scratch_ref(i, ROW_P0)
+          << "))), nrep);\n"
           << "            const double p1 = __ddiv_rn(__dadd_rn(__ldcg(" << scratch_ref(i, ROW_A0 + 1) << "), __dmul_rn(run, __ldcg(" << scratch_ref(i, ROW_P1)
           << "))), nrep);\n"
           << "            const double p2 = __ddiv_rn(__dadd_rn(__ldcg(" << scratch_ref(i, ROW_A0 + 2) << "), __dmul_rn(run, __ldcg(" << scratch_ref(i, ROW_P2)
@@ -614,7 +705,7 @@ int gibbs_jit_build(const McmcParams &P, const GibbsJitConfig &cfg, std::string 
     if (rc != FS_OK) return rc;
     if (const char *v = std::getenv("FAMSEQ_JIT_VERBOSE"))
         if (v[0] == '1')
-            std::fprintf(stderr, "[famseq] Gibbs JIT tb=%d blocks=%d cached weights of %d members in registers, smem=%zu\n%s\n", cfg.tb,
+            std::fprintf(stderr, "[famseq] Gibbs JIT tb=%d blocks=%d draw thresholds of %d members in registers, smem=%zu\n%s\n", cfg.tb,
                          cfg.blocks, cfg.n_p_reg, smem, log.c_str());
     return FS_OK;
 }

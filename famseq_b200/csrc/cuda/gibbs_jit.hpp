@@ -10,12 +10,13 @@
 
 namespace famseq {
 
-// Per chain and member the sampler caches the normalised conditional weights of the last evaluation (P0 and 1 - P2): for
-// the first n_p_reg members in registers, for the others in thread-private shared-memory columns (see gibbs_jit.cu).
+// Per chain and member the sampler caches the outcome of the last evaluation of the member's full conditional as two integer
+// draw thresholds: for the first n_p_reg members in registers, for the others in thread-private shared-memory columns
+// (see gibbs_jit.cu).
 struct GibbsJitConfig {
     int tb = 0;      // chains (threads) per block
     int blocks = 1;  // resident blocks per SM the register budget is sized for
-    int n_p_reg = 0; // members whose cached weights live in registers
+    int n_p_reg = 0; // members whose thresholds live in registers
 };
 
 // Layout heuristic (overridable with FAMSEQ_JIT_TB / _BLOCKS / _PREG).

@@ -10,6 +10,8 @@
 #include "../host/mcmc_plan.hpp"
 #include "common.cuh"
 
+struct fs_phred_fix; // include/famseq_b200.h
+
 namespace famseq {
 
 // ---- Elston-Stewart (es_kernel.cu) ----------------------------------------------------------------
@@ -63,5 +65,11 @@ cudaError_t launch_mcmc(const McmcParams &P, const BatchPtrs &B, int tb, int bur
 // ---- compact input (engine.cu) ----------------------------------------------------------------------
 // lk[k] = lut[pl[k]] for k < n: expands fs_run_pl input for the kernels that read FP64 likelihoods.
 cudaError_t launch_pl_decode(const uint16_t *pl, const double *lut, double *lk, int64_t n, cudaStream_t stream);
+
+// ---- Phred encoding of posteriors (phred_kernel.cu) --------------------------------------------------------
+// out[k] = packed six-digit Phred code of p[k] (include/famseq_b200.h, FS_PHRED_*); values the device does not decide are
+// appended to `fixes` (index0 + k, exact double), *n_fixes counts them even beyond `capacity`.
+cudaError_t launch_phred_pack(const double *p, uint32_t *out, int64_t n, int64_t index0, struct ::fs_phred_fix *fixes, int64_t capacity,
+                              unsigned long long *n_fixes, cudaStream_t stream);
 
 } // namespace famseq

@@ -8,7 +8,9 @@
 // family.cpp:2230-2257).
 // What does not: libc rand() (one global, never seeded stream) is replaced by counter-based Philox4x32-10.
 // The random word of member i in sweep s of site v is word i%4 of Philox(counter = (s, i/4, v_lo, v_hi),
-// key = seed); s = 0 initialises the genotypes (word % 3), s >= 1 are the sweeps.  A value depends on
+// key = seed); s = 0 initialises the genotypes (word % 3), s >= 1 are the sweeps, whose uniform is
+// rd = ((word >> 1) + 0.5) * 2^-31 (31 bits like rand() / RAND_MAX; it lets the generated kernel of gibbs_jit.cu decide a
+// draw by integer comparisons that are exactly equivalent to rd < w0, rd > 1 - w2).  A value depends on
 // (seed, global site, sweep, member) only: any batch split or GPU count gives the same bytes.
 //
 // A chain is strictly sequential, so the kernel is bound by instruction issue of the few warps whose chain
@@ -273,7 +275,7 @@ __global__ void __launch_bounds__(TB) mcmc_kernel(const __grid_constant__ McmcPa
                 r0 = r1;
                 r1 = r2;
                 r2 = r3;
-                const double rd = ((double)u + 0.5) * (1.0 / 4294967296.0);
+                const double rd = ((double)(u >> 1) + 0.5) * (1.0 / 2147483648.0); // 31 bits, like the reference's rand() / RAND_MAX
                 // rd < w0/sum and rd > 1 - w2/sum decided without the division; a non-positive sum means all-zero
                 // weights in the reference, which then draws genotype 1 (family.cpp:2142-2173)
                 const double thr = rd * sum;

@@ -24,6 +24,49 @@ inline void append_g_slow(std::string &out, double v) {
     out.append(buf, (size_t)n);
 }
 
+// The "%g" text of the number m * 10^(e10 - 5), m a six-digit integer (100000 .. 999999): scientific notation when the
+// decimal exponent is below -4 or at least 6, trailing zeros dropped.  Writes at most 13 characters, returns the length.
+inline int emit_decimal6(char *buf, uint32_t m, int e10) {
+    char d[6];
+    for (int i = 5; i >= 0; i--) {
+        d[i] = (char)('0' + m % 10u);
+        m /= 10u;
+    }
+    int nd = 6; // significant digits left after dropping trailing zeros
+    while (nd > 1 && d[nd - 1] == '0') nd--;
+    int n = 0;
+    if (e10 < -4 || e10 >= 6) { // d.ddddde+XX
+        buf[n++] = d[0];
+        if (nd > 1) {
+            buf[n++] = '.';
+            for (int i = 1; i < nd; i++) buf[n++] = d[i];
+        }
+        buf[n++] = 'e';
+        int x = e10;
+        if (x < 0) {
+            buf[n++] = '-';
+            x = -x;
+        } else {
+            buf[n++] = '+';
+        }
+        if (x >= 100) buf[n++] = (char)('0' + x / 100);
+        buf[n++] = (char)('0' + (x / 10) % 10);
+        buf[n++] = (char)('0' + x % 10);
+    } else if (e10 >= 0) { // e10 + 1 integer digits, then the rest
+        for (int i = 0; i <= e10; i++) buf[n++] = d[i];
+        if (nd > e10 + 1) {
+            buf[n++] = '.';
+            for (int i = e10 + 1; i < nd; i++) buf[n++] = d[i];
+        }
+    } else { // 0.000ddd
+        buf[n++] = '0';
+        buf[n++] = '.';
+        for (int i = -1; i > e10; i--) buf[n++] = '0';
+        for (int i = 0; i < nd; i++) buf[n++] = d[i];
+    }
+    return n;
+}
+
 inline void append_g(std::string &out, double v) {
     static const long double kPow10[28] = {1e0L,  1e1L,  1e2L,  1e3L,  1e4L,  1e5L,  1e6L,  1e7L,  1e8L,  1e9L,
                                            1e10L, 1e11L, 1e12L, 1e13L, 1e14L, 1e15L, 1e16L, 1e17L, 1e18L, 1e19L,
@@ -66,45 +109,8 @@ inline void append_g(std::string &out, double v) {
         m = 100000u;
         e10++;
     }
-    char d[6];
-    for (int i = 5; i >= 0; i--) {
-        d[i] = (char)('0' + m % 10u);
-        m /= 10u;
-    }
-    int nd = 6; // significant digits left after dropping trailing zeros
-    while (nd > 1 && d[nd - 1] == '0') nd--;
     char buf[24];
-    int n = 0;
-    if (e10 < -4 || e10 >= 6) { // d.ddddde+XX
-        buf[n++] = d[0];
-        if (nd > 1) {
-            buf[n++] = '.';
-            for (int i = 1; i < nd; i++) buf[n++] = d[i];
-        }
-        buf[n++] = 'e';
-        int x = e10;
-        if (x < 0) {
-            buf[n++] = '-';
-            x = -x;
-        } else {
-            buf[n++] = '+';
-        }
-        if (x >= 100) buf[n++] = (char)('0' + x / 100);
-        buf[n++] = (char)('0' + (x / 10) % 10);
-        buf[n++] = (char)('0' + x % 10);
-    } else if (e10 >= 0) { // e10 + 1 integer digits, then the rest
-        for (int i = 0; i <= e10; i++) buf[n++] = d[i];
-        if (nd > e10 + 1) {
-            buf[n++] = '.';
-            for (int i = e10 + 1; i < nd; i++) buf[n++] = d[i];
-        }
-    } else { // 0.000ddd
-        buf[n++] = '0';
-        buf[n++] = '.';
-        for (int i = -1; i > e10; i--) buf[n++] = '0';
-        for (int i = 0; i < nd; i++) buf[n++] = d[i];
-    }
-    out.append(buf, (size_t)n);
+    out.append(buf, (size_t)emit_decimal6(buf, m, e10));
 }
 
 } // namespace famseq

@@ -91,6 +91,14 @@ def lib() -> ctypes.CDLL:
         L.fs_run_pl_device.argtypes = [P, ctypes.c_int, I64, P, P, I32, I32, U64, I64, P, P, P, P, P]
         L.fs_get_pl_table.restype = ctypes.c_int
         L.fs_get_pl_table.argtypes = [P, P]
+        L.fs_run_pl_phred.restype = ctypes.c_int
+        L.fs_run_pl_phred.argtypes = [P, ctypes.c_int, I64, P, P, I32, I32, U64, I64, P, P, P, P, P, I64, P]
+        L.fs_phred_encode.restype = ctypes.c_int
+        L.fs_phred_encode.argtypes = [P, I64, P, P, P, I64, P]
+        L.fs_phred_text.restype = ctypes.c_int
+        L.fs_phred_text.argtypes = [ctypes.c_uint32, ctypes.c_char_p]
+        L.fs_phred_text_exact.restype = ctypes.c_int
+        L.fs_phred_text_exact.argtypes = [D, ctypes.c_char_p]
         L.fs_destroy.restype = None
         L.fs_destroy.argtypes = [P]
         L.fs_last_error.restype = ctypes.c_char_p
@@ -119,7 +127,8 @@ def lib() -> ctypes.CDLL:
 EXPORTED_SYMBOLS = ["fs_default_params", "fs_device_count", "fs_create", "fs_destroy", "fs_last_error", "fs_run",
                     "fs_run_device", "fs_get_info", "fs_get_tables", "fs_alloc_pinned", "fs_free_pinned",
                     "fs_last_kernel_ms", "fs_bench_fp64_tflops", "fs_get_es_program", "fs_get_gibbs_kernel", "fs_get_es_kernel", "fs_warmup",
-                    "fs_create_multi", "fs_run_pl", "fs_run_pl_device", "fs_get_pl_table"]
+                    "fs_create_multi", "fs_run_pl", "fs_run_pl_device", "fs_get_pl_table",
+                    "fs_run_pl_phred", "fs_phred_encode", "fs_phred_text", "fs_phred_text_exact"]
 
 
 def _check(rc: int) -> None:
@@ -137,6 +146,35 @@ def _ptr(a):
     if isinstance(a, np.ndarray):
         return a.ctypes.data_as(ctypes.c_void_p)
     return ctypes.c_void_p(int(a))  # raw address (e.g. torch.Tensor.data_ptr())
+
+
+PHRED_FIX_DTYPE = np.dtype([("index", np.int64), ("p", np.float64)])  # fs_phred_fix
+PHRED_KIND_FIX = 3
+PHRED_FIX_SINGLE = 1 << 62
+
+
+def phred_text(code: int) -> str | None:
+    """Text of one packed Phred code (fs_phred_text); None for an exception code (kind FS_PHRED_FIX)."""
+    buf = ctypes.create_string_buffer(16)
+    n = lib().fs_phred_text(int(code), buf)
+    return None if n < 0 else buf.raw[:n].decode()
+
+
+def phred_text_exact(p: float) -> str:
+    """The reference's text of one probability (fs_phred_text_exact: libm log10 + "%g")."""
+    buf = ctypes.create_string_buffer(40)
+    n = lib().fs_phred_text_exact(float(p), buf)
+    return buf.raw[:n].decode()
+
+
+@dataclass
+class PhredResult:
+    post: np.ndarray            # [V][S][3] uint32 packed Phred codes of the pedigree-aware posterior
+    single: np.ndarray | None   # the same for the individual-only posterior, or None
+    gt: np.ndarray
+    status: np.ndarray
+    fixes: np.ndarray           # PHRED_FIX_DTYPE records: values the host formats itself (exact doubles)
+    n_fixes: int                # how many there were (may exceed len(fixes) = the capacity given)
 
 
 @dataclass
@@ -269,6 +307,41 @@ class Engine:
         """fs_run on raw HOST addresses (e.g. pinned torch tensors)."""
         _check(lib().fs_run(self._h, method, V, _ptr(lk_ptr), _ptr(flags_ptr), burn, rep, seed, v_offset, _ptr(post_ptr),
                             _ptr(single_ptr), _ptr(gt_ptr), _ptr(status_ptr)))
+
+    def run_pl_phred(self, method: int, pl, flags=None, burn: int = 1000, rep: int = 100000, seed: int = 0, v_offset: int = 0,
+                     want_single: bool = True, fix_capacity: int = 4096) -> PhredResult:
+        """fs_run_pl_phred: compact input AND compact output (Phred codes, 4 bytes per value)."""
+        pl = np.ascontiguousarray(pl, dtype=np.uint16)
+        if pl.ndim != 3 or pl.shape[1] != self.s or pl.shape[2] != 3:
+            raise ValueError(f"input must be [V][{self.s}][3]")
+        V = pl.shape[0]
+        if flags is not None:
+            flags = np.ascontiguousarray(flags, dtype=np.uint8)
+        out = PhredResult(np.empty((V, self.s, 3), np.uint32), np.empty((V, self.s, 3), np.uint32) if want_single else None,
+                          np.empty((V, self.s), np.uint8), np.empty(V, np.uint8), np.zeros(fix_capacity, PHRED_FIX_DTYPE), 0)
+        n = ctypes.c_int64(0)
+        _check(lib().fs_run_pl_phred(self._h, method, V, _ptr(pl), _ptr(flags), burn, rep, seed, v_offset, _ptr(out.post), _ptr(out.single),
+                                     _ptr(out.gt), _ptr(out.status), _ptr(out.fixes), fix_capacity, ctypes.byref(n)))
+        out.n_fixes = int(n.value)
+        out.fixes = out.fixes[:min(out.n_fixes, fix_capacity)]
+        return out
+
+    def run_pl_phred_raw(self, method: int, V: int, pl_ptr, flags_ptr, post32_ptr, single32_ptr, gt_ptr, status_ptr, fixes_ptr, fix_capacity,
+                         burn=1000, rep=100000, seed=0, v_offset=0) -> int:
+        """fs_run_pl_phred on raw HOST addresses; returns the number of exceptions."""
+        n = ctypes.c_int64(0)
+        _check(lib().fs_run_pl_phred(self._h, method, V, _ptr(pl_ptr), _ptr(flags_ptr), burn, rep, seed, v_offset, _ptr(post32_ptr),
+                                     _ptr(single32_ptr), _ptr(gt_ptr), _ptr(status_ptr), _ptr(fixes_ptr), fix_capacity, ctypes.byref(n)))
+        return int(n.value)
+
+    def phred_encode(self, p, fix_capacity: int = 4096):
+        """fs_phred_encode: (codes uint32 like p, fixes, n_fixes) for an array of probabilities."""
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        out = np.empty(p.shape, np.uint32)
+        fixes = np.zeros(fix_capacity, PHRED_FIX_DTYPE)
+        n = ctypes.c_int64(0)
+        _check(lib().fs_phred_encode(self._h, p.size, _ptr(p), _ptr(out), _ptr(fixes), fix_capacity, ctypes.byref(n)))
+        return out, fixes[:min(int(n.value), fix_capacity)], int(n.value)
 
     def run_pl_raw(self, method: int, V: int, pl_ptr, flags_ptr, post_ptr, single_ptr, gt_ptr, status_ptr, burn=1000,
                    rep=100000, seed=0, v_offset=0) -> None:

@@ -142,6 +142,39 @@ int fs_run_pl_device(fs_engine *e, int method, int64_t V, const uint16_t *d_pl, 
 int fs_get_pl_table(const fs_engine *e, double *out);
 #define FS_PL_TABLE_SIZE 65536
 
+/* Compact output (output half).  The reference's drivers print a posterior p as
+ * fabs(-10 * log10(p)) with ostream's default formatting ("%g", six significant digits), or 99999 when that is +inf
+ * (file.cpp:702-761, :938-997, :1814-1873).  fs_run_pl_phred delivers exactly that, 4 bytes per value instead of 8: the
+ * six decimal digits and the decimal exponent the text is made of, computed on the device.
+ *   bits  0-19  m    six-digit integer 100000 .. 999999                         (kind FS_PHRED_NUMBER)
+ *   bits 20-25  e+32 decimal exponent of the leading digit: value = m * 10^(e-5)
+ *   bits 30-31  kind FS_PHRED_NUMBER 0 | FS_PHRED_ZERO (p = 1, prints "0") | FS_PHRED_INF (p = 0, prints "99999") |
+ *                    FS_PHRED_FIX: the device did not decide this one (it sits within 3e-8 of a rounding boundary in the
+ *                    sixth digit, where glibc's and CUDA's log10 could round differently, or p is not in [0, 1]); its index
+ *                    and exact double come back in `fixes` and the host formats it the reference's way.  ~6 in 10^8.
+ * fs_phred_text() turns a code into the text; tests compare it with the reference's formatting of the FP64 results. */
+#define FS_PHRED_NUMBER 0u
+#define FS_PHRED_ZERO (1u << 30)
+#define FS_PHRED_INF (2u << 30)
+#define FS_PHRED_FIX (3u << 30)
+typedef struct fs_phred_fix {
+    int64_t index; /* position in the [V][S][3] array; + FS_PHRED_FIX_SINGLE for an entry of `single_phred` */
+    double p;      /* the exact probability */
+} fs_phred_fix;
+#define FS_PHRED_FIX_SINGLE ((int64_t)1 << 62)
+/* Like fs_run_pl, with the posteriors Phred-encoded: post_phred, single_phred [V][S][3] uint32 (single_phred may be
+ * NULL).  Up to `fix_capacity` exceptions are written to `fixes`; *n_fixes receives how many there were -- when it exceeds
+ * the capacity the caller has to repeat the call with more room (or take fs_run_pl). */
+int fs_run_pl_phred(fs_engine *e, int method, int64_t V, const uint16_t *pl, const uint8_t *flags, int32_t burn, int32_t rep,
+                    uint64_t seed, int64_t v_offset, uint32_t *post_phred, uint32_t *single_phred, uint8_t *gt, uint8_t *status,
+                    fs_phred_fix *fixes, int64_t fix_capacity, int64_t *n_fixes);
+/* The encoder on its own: n probabilities on the HOST in, n codes out (device round trip inside). */
+int fs_phred_encode(fs_engine *e, int64_t n, const double *p, uint32_t *out, fs_phred_fix *fixes, int64_t fix_capacity, int64_t *n_fixes);
+/* Text of a code (at most 13 characters + NUL) into buf; returns its length, or -1 for FS_PHRED_FIX.  Host only. */
+int fs_phred_text(uint32_t code, char *buf);
+/* The reference's text of one probability (the formatting fs_phred_fix entries need): libm log10 + "%g".  Host only. */
+int fs_phred_text_exact(double p, char *buf);
+
 /* Introspection of the compiled pedigree program (all fields are counts). */
 typedef struct fs_info {
     int32_t n, s;             /* members, sequenced columns                                          */

@@ -9,6 +9,7 @@
 #include "famseq_oracle.h"
 
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -439,6 +440,14 @@ void fso_pl_table(double *out, int n) {
     for (int k = 0; k < n; k++) out[k] = fso_pl_decode((double)k);
 }
 
+/* file.cpp:702-749 (= :938-997, :1814-1873): a posterior is printed as fabs(-10*log10(p)) through ostream's default
+ * formatting (printf's %g, six significant digits), or as 99999 when -10*log10(p) is +infinity. */
+int fso_phred_text(double p, char *buf) {
+    const double v = -10 * log10(p);
+    if (v == INFINITY) return sprintf(buf, "99999");
+    return sprintf(buf, "%g", fabs(v));
+}
+
 void fso_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
     uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
     for (int r = 0; r < 10; r++) {
@@ -496,7 +505,7 @@ static int rng_init_genotype(rng_t *r, int member) {
 
 static double rng_uniform(rng_t *r, int sweep, int member) {
     if (r->kind == FSO_RNG_LIBC) return (double)rand() / (double)RAND_MAX; /* family.cpp:2161 */
-    return ((double)rng_u32(r, sweep, member) + 0.5) * (1.0 / 4294967296.0);
+    return ((double)(rng_u32(r, sweep, member) >> 1) + 0.5) * (1.0 / 2147483648.0); /* 31 bits, like rand() / RAND_MAX */
 }
 
 /* Test probe: smallest and largest weight sum `s` met by the chains of the last fso_run(MCMC) call (all its variants).

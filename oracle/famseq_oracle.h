@@ -62,6 +62,10 @@ double fso_pl_decode(double x);
 /* ... for every integer PL 0 .. n-1 at once (the table the engine's fs_run_pl decodes through). */
 void fso_pl_table(double *out, int n);
 
+/* The drivers' Phred text of one posterior (file.cpp:702-749): "%g" of fabs(-10*log10(p)), "99999" for +inf.
+ * buf needs 32 bytes; returns the length. */
+int fso_phred_text(double p, char *buf);
+
 /* Test probe: {min, max} of the Gibbs weight sums met during the last fso_run(FSO_MCMC) call (over all its variants). */
 void fso_mcmc_sum_range(double out[2]);
 /* Test probe: {Gibbs steps, steps that changed the member's genotype} of the last fso_run(FSO_MCMC) call. */

@@ -59,6 +59,8 @@ def lib() -> ctypes.CDLL:
         L.fso_pl_decode.argtypes = [ctypes.c_double]
         L.fso_pl_table.restype = None
         L.fso_pl_table.argtypes = [P, ctypes.c_int]
+        L.fso_phred_text.restype = ctypes.c_int
+        L.fso_phred_text.argtypes = [ctypes.c_double, ctypes.c_char_p]
         L.fso_mcmc_sum_range.restype = None
         L.fso_mcmc_sum_range.argtypes = [P]
         L.fso_philox4x32.restype = None
@@ -145,6 +147,13 @@ def run(ped: Pedigree, cols, lk, flags=None, method=ES, mrate=1e-7, lc=1.0, prio
     if rc != 0:
         raise RuntimeError(f"oracle error {rc}")
     return dict(post=post, single=single, gt=gt, status=status, post_full=pf, single_full=sf)
+
+
+def phred_text(p: float) -> str:
+    """The reference drivers' text of one posterior (file.cpp:702-749)."""
+    buf = ctypes.create_string_buffer(40)
+    n = lib().fso_phred_text(float(p), buf)
+    return buf.raw[:n].decode()
 
 
 def mcmc_sum_range():

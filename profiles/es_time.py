@@ -1,0 +1,45 @@
+"""Times ES kernels device-resident on nuclear families with C children (quads, sibships) and on named pedigrees:
+    python profiles/es_time.py nuclear 2 5000000        python profiles/es_time.py ped14 1000000
+Prints variants/s and the fraction of the HBM roofline (73 S + 2 bytes per variant).  Tuning aid, not a bench value."""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import famseq_b200 as fs  # noqa: E402
+from famseq_b200 import synth  # noqa: E402
+
+what = sys.argv[1]
+if what == "nuclear":
+    C, V = int(sys.argv[2]), int(sys.argv[3])
+    ped = synth._mk([(1, 0, 0, 1), (2, 0, 0, 2)] + [(3 + k, 2, 1, 1 + k % 2) for k in range(C)])
+else:
+    ped, V = synth.PEDIGREES[what](), int(sys.argv[2])
+lk, fl = synth.synth_likelihoods(ped, V, 20261018 + 2)
+S = lk.shape[1]
+d_lk, d_fl = torch.from_numpy(lk).cuda(), torch.from_numpy(fl).cuda()
+d_post = torch.empty((V, S, 3), dtype=torch.float64, device="cuda")
+d_single = torch.empty_like(d_post)
+d_gt = torch.empty((V, S), dtype=torch.uint8, device="cuda")
+d_st = torch.empty(V, dtype=torch.uint8, device="cuda")
+peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6538.0
+with fs.Engine(ped.ids, ped.mids, ped.fids, ped.genders, ped.sequenced_cols(), device=0) as e:
+    def step():
+        e.run_device(fs.ES, V, d_lk.data_ptr(), d_fl.data_ptr(), d_post.data_ptr(), d_single.data_ptr(), d_gt.data_ptr(), d_st.data_ptr(),
+                     stream=torch.cuda.current_stream().cuda_stream)
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    info = e.info()
+gbs = (73 * S + 2) * V / ms / 1e6
+print(f"{' '.join(sys.argv[1:])}: S={S} {V / ms * 1e3:.4g} variants/s, {ms:.3f} ms, {gbs:.0f} GB/s = {gbs / peak:.3f} of HBM, jit_launches={info['jit_launches']}")

@@ -1,5 +1,8 @@
 """Times the MCMC kernels on one pedigree, device-resident (CUDA events), for tuning sweeps:
-    FAMSEQ_JIT_PREG=.. FAMSEQ_JIT_TB=.. python profiles/mcmc_time.py [ped40] [variants] [burn] [rep] [lk: synth|flat|partial]
+    FAMSEQ_JIT_PREG=.. FAMSEQ_JIT_TB=.. python profiles/mcmc_time.py [ped40] [variants] [burn] [rep] [lk: synth|flat|partial|random]
+synth = the bench's data (genotypes dropped through the pedigree); flat = the same with flattened likelihoods; partial = every
+third member sequenced; random = likelihoods of unrelated individuals (Mendelian inconsistencies everywhere: the chains
+keep moving -- the worst case of the cached-conditional kernel).
 Prints one line: pedigree, kernel, variants/s.  Not a bench value (no clocks sampling, short)."""
 import os
 import sys
@@ -20,9 +23,13 @@ rep = int(sys.argv[4]) if len(sys.argv) > 4 else 10000
 kind = sys.argv[5] if len(sys.argv) > 5 else "synth"
 ped = synth.PEDIGREES[name]()
 cols = ped.sequenced_cols()
+if kind == "random":
+    lk, fl = synth.synth_likelihoods(synth._mk([(i, 0, 0, 1) for i in range(1, len(cols) + 1)]), V, 20261018 + 3)
+else:
+    lk, fl = synth.synth_likelihoods(ped, V, 20261018 + 3)
 if kind == "partial":  # every third member sequenced: the others flip all the time
     cols = cols[::3]
-lk, fl = synth.synth_likelihoods(synth._mk([(i, 0, 0, 1) for i in range(1, len(cols) + 1)]), V, 20261018 + 3)
+    lk = np.ascontiguousarray(lk[:, ::3])
 if kind == "flat":
     lk = np.sqrt(np.sqrt(lk))
 S = len(cols)

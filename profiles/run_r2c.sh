@@ -16,4 +16,7 @@ python profiles/mcmc_time.py ped14 500000
 python profiles/mcmc_time.py trio 2000000 100 1000
 } > gpurun_out/r2c_mcmc_sweep.log 2>&1
 cat gpurun_out/r2c_mcmc_sweep.log | cut -c 1-220
+for c in 2 3 5; do python profiles/es_time.py nuclear $c 4000000; done >> gpurun_out/r2c_mcmc_sweep.log 2>&1
+FAMSEQ_ES_JIT=1 python profiles/es_time.py ped14 1000000 >> gpurun_out/r2c_mcmc_sweep.log 2>&1
+tail -4 gpurun_out/r2c_mcmc_sweep.log
 python bench.py --steps 10 --warmup 3 --methods es --no-cpu-baseline > gpurun_out/r2c_bench.json 2> gpurun_out/r2c_bench.err; echo "bench rc=$?"

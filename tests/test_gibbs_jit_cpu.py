@@ -25,6 +25,7 @@ typedef unsigned int u32; typedef unsigned long long u64; typedef long long i64;
 #define __global__
 #define __constant__ static const
 #define __forceinline__ inline
+#define __noinline__ __attribute__((noinline))
 #define __launch_bounds__(...)
 #define __align__(n)
 #define __shared__
@@ -40,6 +41,9 @@ static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dsub_rn(double a, double b) { return a - b; }
 static inline double __ddiv_rn(double a, double b) { return a / b; }
+static inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
+static inline u32 __double2uint_ru(double x) { const double c = std::ceil(x); return c <= 0.0 ? 0u : (c >= 4294967295.0 ? 4294967295u : (u32)c); }
+static inline int __double2int_rd(double x) { return (int)std::floor(x); }
 static inline double __longlong_as_double(long long x) { double d; std::memcpy(&d, &x, 8); return d; }
 static inline int __double2hiint(double d) { long long x; std::memcpy(&x, &d, 8); return (int)(x >> 32); }
 static inline double __hiloint2double(int hi, int lo) { long long x = ((long long)hi << 32) | (unsigned)lo; double d; std::memcpy(&d, &x, 8); return d; }

@@ -129,7 +129,9 @@ def test_generated_gibbs_kernel_compiles_for_sm_100a(name):
     ped = synth.PEDIGREES[name]()
     with fs.Engine(ped.ids, ped.mids, ped.fids, ped.genders, ped.sequenced_cols(), device=-1) as e:
         src, _ = e.gibbs_kernel()
-        assert src.count("// member ") == 2 * ped.n  # one copy of the sweep with the autosomal, one with the chrX rules
+        # one evaluation function per member and rule set (autosomal, chrX), called from the member-by-member path of its group
+        for i in range(ped.n):
+            assert src.count(f"Rc eval_a_{i}(") == 1 and src.count(f"Rc eval_x_{i}(") == 1 and src.count(f"= eval_a_{i}(") == 1
         assert 'extern "C" __global__' in src and "famseq_gibbs" in src
         log, cubin_bytes = e.gibbs_kernel(compile=True)
     assert cubin_bytes > 0
@@ -211,3 +213,25 @@ def test_multi_device_argument_checks():
         with pytest.raises(fs.FamSeqError) as ei:
             fs.Engine(ped.ids, ped.mids, ped.fids, ped.genders, ped.sequenced_cols(), device=devices)
         assert ei.value.code == -1
+
+
+def test_phred_code_text_is_printf_g():
+    """fs_phred_text: the text of a packed Phred code (six digits m, decimal exponent e: value m * 10^(e-5)) must be what
+    "%g" prints for that number -- every exponent the codes can carry, trailing-zero and notation rules included."""
+    rng = np.random.default_rng(7)
+    for e in range(-20, 8):
+        for m in list(rng.integers(100000, 1000000, 200)) + [100000, 999999, 100001, 500000, 120000, 123000, 123400, 123450]:
+            code = int(m) | ((e + 32) << 20)
+            want = "%g" % float(f"{int(m)}e{e - 5}")
+            assert fs.phred_text(code) == want, (m, e, fs.phred_text(code), want)
+    assert fs.phred_text(1 << 30) == "0" and fs.phred_text(2 << 30) == "99999" and fs.phred_text(3 << 30) is None
+
+
+def test_exact_phred_text_matches_the_oracle():
+    """fs_phred_text_exact (what a caller formats fs_phred_fix entries with) against the oracle's restatement of
+    file.cpp:702-749, including 0, 1, subnormals, NaN and values above one."""
+    rng = np.random.default_rng(11)
+    ps = np.concatenate([rng.random(3000), 10.0 ** (-320 * rng.random(3000)), 1 - 10.0 ** (-16 * rng.random(3000)),
+                         [0.0, 1.0, 5e-324, 2.2e-308, 0.5, np.nan, -0.25, 1.5, np.inf, -0.0]])
+    for p in ps:
+        assert fs.phred_text_exact(p) == O.phred_text(p), p
