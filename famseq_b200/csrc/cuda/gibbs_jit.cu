@@ -148,6 +148,11 @@ std::vector<Member> decode(const McmcPlan &pl) {
     return m;
 }
 
+// ================================================================================================================
+// Generator 1: cached full conditionals (the default where most members are sequenced; see the header of this file)
+// ================================================================================================================
+namespace cached {
+
 // Where the cached draw thresholds (T0, T2: two 32-bit words) of every member live: the first n_p_reg members in registers,
 // the others in thread-private shared-memory columns.  Per member, seven rows of the block-private global scratch hold the
 // three accumulators, P0, P1, P2 and the sweep index of the last evaluation.
@@ -354,11 +359,10 @@ void emit_sweep(std::ostringstream &o, const std::vector<Member> &M, const Layou
     }
 }
 
-} // namespace
-
-GibbsJitConfig gibbs_jit_default_config(const McmcParams &P) {
+GibbsJitConfig default_config(const McmcParams &P) {
     const int n = P.plan.n;
     GibbsJitConfig c;
+    c.cached = 1;
     // A chain needs ~60 registers for the step itself, one per member for the genotypes and two per member whose draw
     // thresholds sit in registers; the other members' pairs go to thread-private shared-memory columns (8 bytes per member
     // and chain).  The block is as large as the register file allows (the step is a chain of short integer dependencies:
@@ -374,7 +378,7 @@ GibbsJitConfig gibbs_jit_default_config(const McmcParams &P) {
     return c;
 }
 
-std::string gibbs_jit_source(const McmcParams &P, const GibbsJitConfig &cfg) {
+std::string source(const McmcParams &P, const GibbsJitConfig &cfg) {
     const RunConstants &C = P.C;
     const std::vector<Member> M = decode(P.plan);
     const int n = (int)M.size(), S = C.s, words = (n + 31) / 32;
@@ -526,6 +530,427 @@ std::string gibbs_jit_source(const McmcParams &P, const GibbsJitConfig &cfg) {
     return o.str();
 }
 
+} // namespace cached
+
+// ================================================================================================================
+// Generator 2: dense sweeps -- every full conditional evaluated in every step (round 1's kernel).  Its speed does not depend
+// on the data, so it is the choice where the chains keep moving: pedigrees with many unsequenced members.  A sweep is ONE
+// basic block of ~50 instructions per member; per chain, 3 own factors (1e6 * prior * lk) and 3 Rao-Blackwell accumulators
+// per member are placed in registers, in thread-private shared-memory columns, or in a block-private scratch that stays in
+// L2 (own factors through a software prefetch queue, accumulators through red.global.add.f64).  Same chains as the other
+// two kernels; accumulates sweep by sweep like the table-driven kernel (same bytes as that one).
+// ================================================================================================================
+namespace dense {
+
+enum Place { REG, SMEM, GLOB };
+
+// Where the 3 own factors and the 3 accumulators of every member live.  Members are assigned in ped order: registers
+// first, then shared-memory rows, the rest in the block-private global scratch (own factors: read through a software
+// prefetch queue; accumulators: fire-and-forget red.global.add.f64).
+struct Layout {
+    int n = 0;
+    std::vector<Place> lk_place, acc_place;
+    std::vector<int> lk_row, acc_row; // row (3-vector) in the shared-memory area or in the scratch
+    int smem_rows = 0, glob_rows = 0;
+    std::vector<int> lk_glob; // members whose own factors come from the scratch, in ped order
+    int depth = 1;            // prefetch distance, in such members
+};
+
+// Members that go to the scratch are spread evenly over the sweep (so that a short prefetch queue covers the L2
+// latency and the reductions do not bunch up); of the others, the first n_reg sit in registers, the rest in shared memory.
+std::vector<Place> spread(int n, int n_reg, int n_smem) {
+    std::vector<Place> place(n, SMEM);
+    const int n_glob = std::max(0, n - n_reg - n_smem);
+    for (int i = 0; i < n; i++)
+        if ((long)(i + 1) * n_glob / n != (long)i * n_glob / n) place[i] = GLOB;
+    int left = n_reg;
+    for (int i = 0; i < n && left > 0; i++)
+        if (place[i] != GLOB) {
+            place[i] = REG;
+            left--;
+        }
+    return place;
+}
+
+Layout make_layout(int n, const GibbsJitConfig &cfg) {
+    Layout L;
+    L.n = n;
+    L.acc_place = spread(n, cfg.n_acc_reg, cfg.n_acc_smem);
+    L.lk_place = spread(n, cfg.n_lk_reg, cfg.n_lk_smem);
+    L.lk_row.assign(n, -1);
+    L.acc_row.assign(n, -1);
+    for (int i = 0; i < n; i++) {
+        if (L.acc_place[i] == SMEM) L.acc_row[i] = L.smem_rows++;
+        if (L.acc_place[i] == GLOB) L.acc_row[i] = L.glob_rows++;
+    }
+    for (int i = 0; i < n; i++) {
+        if (L.lk_place[i] == SMEM) L.lk_row[i] = L.smem_rows++;
+        if (L.lk_place[i] == GLOB) {
+            L.lk_row[i] = L.glob_rows++;
+            L.lk_glob.push_back(i);
+        }
+    }
+    L.depth = std::max(1, cfg.prefetch);
+    return L;
+}
+
+size_t smem_bytes(const Layout &L, int tb) { return (size_t)kTabBytes + (size_t)L.smem_rows * 3 * tb * 8; }
+
+std::string smem_ref(int row, int g) { return "sa[" + std::to_string(row * 3 + g) + " * TB]"; }
+std::string glob_ref(int row, int g) { return "wg + " + std::to_string(row * 3 + g) + " * TB"; }
+
+// One Gibbs step of member i (family.cpp:2113-2178 / :2195-2295), as straight-line code.
+// `row` names three variables that hold the member's transmission row T[.][mother][father] (loaded by emit_sweep,
+// shared by consecutive full sibs).
+// chrX sweeps (family.cpp:2183-2297): a member's own transmission comes from the table of its sex, a child's from the
+// table of the child's sex, and only males get the children factor.
+const char *table_of(bool chrx, bool male) { return chrx ? (male ? "tXM" : "tXF") : "tA"; }
+
+void emit_member(std::ostringstream &o, const std::vector<Member> &M, const Layout &L, int i, bool accumulate, const std::string &row,
+                 bool chrx) {
+    const Member &m = M[i];
+    o << "            { // member " << i << (m.founder ? " (founder" : " (child of ") ;
+    if (!m.founder) o << m.mother << " x " << m.father;
+    o << (m.male ? ", male)\n" : ", not male)\n");
+    if (L.lk_place[i] == GLOB) {
+        const int G = (int)L.lk_glob.size();
+        const int k = (int)(std::find(L.lk_glob.begin(), L.lk_glob.end(), i) - L.lk_glob.begin());
+        const int slot = k % L.depth, ahead = L.lk_glob[(k + L.depth) % G];
+        o << "                double w0 = q" << slot << "_0, w1 = q" << slot << "_1, w2 = q" << slot << "_2;\n";
+        o << "                q" << slot << "_0 = __ldcg(" << glob_ref(L.lk_row[ahead], 0) << "); q" << slot << "_1 = __ldcg("
+          << glob_ref(L.lk_row[ahead], 1) << "); q" << slot << "_2 = __ldcg(" << glob_ref(L.lk_row[ahead], 2) << ");\n";
+    } else if (L.lk_place[i] == SMEM) {
+        o << "                double w0 = " << smem_ref(L.lk_row[i], 0) << ", w1 = " << smem_ref(L.lk_row[i], 1) << ", w2 = "
+          << smem_ref(L.lk_row[i], 2) << ";\n";
+    } else {
+        o << "                double w0 = W" << i << "_0, w1 = W" << i << "_1, w2 = W" << i << "_2;\n";
+    }
+    if (!m.founder) // transmission from the parents' current genotypes
+        o << "                w0 = __dmul_rn(w0, " << row << "_0); w1 = __dmul_rn(w1, " << row << "_1); w2 = __dmul_rn(w2, " << row << "_2);\n";
+    for (const Member::Link &l : m.links) {
+        if (chrx && !m.male) break; // family.cpp:2230-2257
+        const char *tA = table_of(chrx, l.child_male);
+        if (m.male) // this member is the father: entry child*9 + mother*3 + g
+            o << "                { const u32 ta = " << tA << " + o" << l.child << " * 9u + o" << l.other << " * 3u;\n"
+              << "                  w0 = __dmul_rn(w0, lds64(ta)); w1 = __dmul_rn(w1, lds64(ta + " << kRow
+              << ")); w2 = __dmul_rn(w2, lds64(ta + " << 2 * kRow << ")); }\n";
+        else // this member is the mother: entry child*9 + g*3 + father
+            o << "                { const u32 ta = " << tA << " + o" << l.child << " * 9u + o" << l.other << ";\n"
+              << "                  w0 = __dmul_rn(w0, lds64(ta)); w1 = __dmul_rn(w1, lds64(ta + " << 3 * kRow
+              << ")); w2 = __dmul_rn(w2, lds64(ta + " << 6 * kRow << ")); }\n";
+    }
+    o << "                const double sum = __dadd_rn(__dadd_rn(w0, w1), w2);\n";
+    if ((i & 3) == 0) o << "                philox((u32)sweep, " << (i >> 2) << "u, gv_lo, gv_hi, k0, k1, r0, r1, r2, r3);\n";
+    // ((r >> 1) + 0.5) * 2^-31 = (r | 1) * 2^-32 without an int-to-double conversion: 1 + (r | 1) * 2^-32 assembled from bits, minus 1 (exact)
+    o << "                const double rd = __dsub_rn(__hiloint2double((int)(0x3ff00000u | ((r" << (i & 3) << " | 1u) >> 12)), (int)((r" << (i & 3)
+      << " | 1u) << 20)), 1.0);\n";
+    o << "                const double thr = __dmul_rn(rd, sum);\n";
+    // The straight-line code assumes a positive normal sum with exponent in [-963, 963) (no sign test, Newton reciprocal);
+    // `worst` records whether that ever failed, in which case the chain is redone by the table-driven kernel.
+    o << "                worst = max(worst, (u32)__double2hiint(sum) - 0x03c00000u);\n";
+    o << "                o" << i << " = (thr < w0) ? 0u : ((thr > __dsub_rn(sum, w2)) ? " << 2 * kRow << "u : " << kRow << "u);\n";
+    if (accumulate) {
+        o << "                const double inv = newton_reciprocal(sum);\n";
+        for (int g = 0; g < 3; g++) {
+            const std::string term = "__dmul_rn(w" + std::to_string(g) + ", inv)";
+            if (L.acc_place[i] == SMEM)
+                o << "                " << smem_ref(L.acc_row[i], g) << " = __dadd_rn(" << smem_ref(L.acc_row[i], g) << ", " << term << ");\n";
+            else if (L.acc_place[i] == GLOB)
+                o << "                atomicAdd(" << glob_ref(L.acc_row[i], g) << ", " << term << ");\n";
+            else
+                o << "                A" << i << "_" << g << " = __dadd_rn(A" << i << "_" << g << ", " << term << ");\n";
+        }
+    }
+    o << "            }\n";
+}
+
+// One sweep over the members in ped order.  A non-founder's own factor needs the row T[g][mother][father], g = 0..2
+// (entry g*9 + mother*3 + father): full sibs that follow each other before either parent is updated again share one
+// look-up -- three shared-memory loads saved per sib, and shared-memory bandwidth is what bounds this kernel.
+void emit_sweep(std::ostringstream &o, const std::vector<Member> &M, const Layout &L, bool accumulate, bool chrx, const char *tag) {
+    const int n = (int)M.size();
+    std::vector<int> version(n, 0);
+    struct Row {
+        int mother, father, vm, vf;
+        bool male;
+        std::string name;
+    };
+    std::vector<Row> rows;
+    for (int i = 0; i < n; i++) {
+        std::string row;
+        if (!M[i].founder) {
+            const int mo = M[i].mother, fa = M[i].father;
+            for (const Row &r : rows)
+                if (r.mother == mo && r.father == fa && r.vm == version[mo] && r.vf == version[fa] && (!chrx || r.male == M[i].male))
+                    row = r.name;
+            if (row.empty()) {
+                row = std::string("T") + tag + std::to_string(i);
+                o << "            const u32 a" << row << " = " << table_of(chrx, M[i].male) << " + o" << mo << " * 3u + o" << fa << ";\n";
+                o << "            const double " << row << "_0 = lds64(a" << row << "), " << row << "_1 = lds64(a" << row << " + " << 9 * kRow << "), "
+                  << row << "_2 = lds64(a" << row << " + " << 18 * kRow << ");\n";
+                rows.push_back({mo, fa, version[mo], version[fa], M[i].male, row});
+            }
+        }
+        emit_member(o, M, L, i, accumulate, row, chrx);
+        version[i]++;
+    }
+}
+
+// End of a sweep: the loads in flight belong to the first members of the next sweep; put them where it expects them.
+void emit_queue_rotation(std::ostringstream &o, const Layout &L) {
+    const int G = (int)L.lk_glob.size(), D = L.depth;
+    if (G == 0 || G % D == 0) return;
+    o << "            { // prefetch queue: slot j of the next sweep is slot (j + " << G % D << ") % " << D << " of this one\n";
+    for (int j = 0; j < D; j++)
+        for (int g = 0; g < 3; g++) o << "                const double t" << j << "_" << g << " = q" << (G + j) % D << "_" << g << ";\n";
+    for (int j = 0; j < D; j++)
+        for (int g = 0; g < 3; g++) o << "                q" << j << "_" << g << " = t" << j << "_" << g << ";\n";
+    o << "            }\n";
+}
+
+GibbsJitConfig default_config(const McmcParams &P) {
+    const int n = P.plan.n;
+    GibbsJitConfig c;
+    // Two warps per SM sub-partition: 256 chains per SM, up to 255 registers each.  Measured on the 40-member pedigree
+    // (profiles/jit_sweep*.sh): registers are the only free storage -- a shared-memory row costs LDS bandwidth (the unit
+    // that bounds the kernel), an accumulator in L2 costs three reductions (the L2 sustains ~6.5e11 FP64 reductions/s
+    // per GPU), own factors in L2 cost three loads.  So: accumulators in registers as far as they go (the step itself
+    // needs ~124 + n), a sixth of the shared-memory rows for more accumulators, the rest of them for own factors, and
+    // whatever is left in L2.
+    c.tb = 256;
+    c.blocks = 1;
+    c.prefetch = 2;
+    const int reg_rows = std::max(0, (254 - (124 + n)) / 6);
+    const int smem_rows = (int)((kSmemPerBlockMax - kTabBytes) / ((size_t)24 * c.tb));
+    c.n_acc_reg = std::min(n, reg_rows);
+    c.n_lk_reg = std::min(n, reg_rows - c.n_acc_reg);
+    c.n_acc_smem = std::min(n - c.n_acc_reg, smem_rows / 6);
+    c.n_lk_smem = std::min(n - c.n_lk_reg, smem_rows - c.n_acc_smem);
+    if (c.n_acc_reg == n && c.n_lk_reg == n) // small pedigree, everything in registers: more than one block per SM
+        c.blocks = std::max(1, std::min(4, 65536 / (c.tb * (70 + n + 12 * n))));
+    c.cached = 0;
+    c.tb = env_int("FAMSEQ_JIT_TB", c.tb);
+    c.blocks = std::max(1, env_int("FAMSEQ_JIT_BLOCKS", c.blocks));
+    c.prefetch = std::max(1, env_int("FAMSEQ_JIT_PF", c.prefetch));
+    c.n_acc_reg = std::min(n, std::max(0, env_int("FAMSEQ_JIT_RACC", c.n_acc_reg)));
+    c.n_acc_smem = std::min(n - c.n_acc_reg, std::max(0, env_int("FAMSEQ_JIT_SACC", c.n_acc_smem)));
+    c.n_lk_reg = std::min(n, std::max(0, env_int("FAMSEQ_JIT_RLK", c.n_lk_reg)));
+    c.n_lk_smem = std::min(n - c.n_lk_reg, std::max(0, env_int("FAMSEQ_JIT_SLK", c.n_lk_smem)));
+    return c;
+}
+
+std::string source(const McmcParams &P, const GibbsJitConfig &cfg) {
+    const RunConstants &C = P.C;
+    const std::vector<Member> M = decode(P.plan);
+    const int n = (int)M.size(), S = C.s;
+    const Layout L = make_layout(n, cfg);
+    std::ostringstream o;
+    o << "// generated by famseq_b200 (gibbs_jit.cu, dense sweeps) for one pedigree: " << n << " members, " << S << " input columns\n";
+    o << "// layout: " << cfg.tb << " chains per block; accumulators " << cfg.n_acc_reg << " reg / " << cfg.n_acc_smem << " smem / "
+      << n - cfg.n_acc_reg - cfg.n_acc_smem << " L2; own factors " << cfg.n_lk_reg << " reg / " << cfg.n_lk_smem << " smem / "
+      << L.lk_glob.size() << " L2 (prefetch " << L.depth << ")\n";
+    o << "#define TB " << cfg.tb << "\n#define NCOL " << S << "\n";
+    o << kPrelude;
+    o << "__constant__ u64 TAB_BITS[81] = {";
+    for (int t = 0; t < 3; t++)
+        for (int k = 0; k < 27; k++) o << (t + k ? ", " : "") << bits(C.tab[t][k]);
+    o << "};\n__constant__ u64 PRIOR_BITS[12] = {";
+    for (int t = 0; t < 4; t++)
+        for (int g = 0; g < 3; g++) o << (t + g ? ", " : "") << bits(C.prior[t][g]);
+    o << "};\n__constant__ u8 COL_MALE[NCOL + 1] = {";
+    for (int c = 0; c < S; c++) o << (int)C.col_male[c] << ", ";
+    o << "0};\n";
+    const unsigned unseq = (C.unseq_fail[0] ? 1u : 0u) | (C.unseq_fail[1] ? 2u : 0u) | (C.unseq_fail[2] ? 4u : 0u) | (C.unseq_fail[3] ? 8u : 0u);
+
+    o << "\nextern \"C\" __global__ void __launch_bounds__(TB, " << cfg.blocks << ")\n"
+      << "famseq_gibbs(const double *__restrict__ lk, const u8 *__restrict__ flags, double *__restrict__ post,\n"
+      << "             double *__restrict__ single, u8 *__restrict__ gt, u8 *__restrict__ status, i64 V, int burn, int rep,\n"
+      << "             u64 seed, i64 v_offset, double *scratch, int n_tiles) {\n"
+      << "    extern __shared__ __align__(16) unsigned char smem_raw[];\n"
+      << "    double *s_tab = (double *)smem_raw;              // [81][" << kCopies << "]\n"
+      << "    double *s_vec = s_tab + 81 * " << kCopies << ";           // [" << L.smem_rows << " * 3][TB] thread-private columns\n"
+      << "    const int tid = threadIdx.x, lane = tid & 31;\n"
+      << "    for (int e = tid; e < 81 * " << kCopies << "; e += TB) s_tab[e] = __longlong_as_double((i64)TAB_BITS[e / " << kCopies << "]);\n"
+      << "    __syncthreads();\n"
+      << "    u32 tab_addr = (u32)__cvta_generic_to_shared(s_tab) + (u32)(lane & " << (kCopies - 1) << ") * 8u;\n"
+      << "    asm volatile(\"\" : \"+r\"(tab_addr) :: \"memory\"); // table reads stay below the barrier\n"
+      << "    double *sa = s_vec + tid;\n"
+      << "    double *wg = scratch + (size_t)blockIdx.x * " << std::max(1, L.glob_rows) * 3 << " * TB + tid; // [row][g][TB], block-private\n"
+      << "    const u32 k0 = (u32)seed, k1 = (u32)(seed >> 32);\n"
+      << "    const double lrc = __longlong_as_double((i64)" << bits(C.lrc) << ");\n"
+      << "    (void)sa; (void)wg;\n\n"
+      << "    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {\n"
+      << "        const i64 v = (i64)tile * TB + tid;\n"
+      << "        if (v >= V) continue;\n"
+      << "        const u32 flag = flags ? flags[v] : 0u;\n"
+      << "        const bool known = flag & 1u, chrx = (flag >> 1) & 1u;\n"
+      << "        const double pa0 = __longlong_as_double((i64)PRIOR_BITS[known ? 3 : 0]), pa1 = __longlong_as_double((i64)PRIOR_BITS[known ? 4 : 1]),\n"
+      << "                     pa2 = __longlong_as_double((i64)PRIOR_BITS[known ? 5 : 2]);\n"
+      << "        const double pm0 = chrx ? __longlong_as_double((i64)PRIOR_BITS[known ? 9 : 6]) : pa0, pm1 = chrx ? __longlong_as_double((i64)PRIOR_BITS[known ? 10 : 7]) : pa1,\n"
+      << "                     pm2 = chrx ? __longlong_as_double((i64)PRIOR_BITS[known ? 11 : 8]) : pa2;\n"
+      << "        const double *lkv = lk + v * (NCOL * 3);\n"
+      << "        double *gp = post + v * (NCOL * 3), *gs = single + v * (NCOL * 3);\n"
+      << "        u8 *gg = gt + v * NCOL;\n"
+      << "        // individual-only posterior + LRC gate (family.cpp:1940-1971)\n"
+      << "        bool failed = (" << unseq << "u >> (flag & 3u)) & 1u;\n"
+      << "        bool pedigree_needed = false;\n"
+      << "        for (int c = 0; c < NCOL; c++) {\n"
+      << "            const double l0 = lkv[c * 3], l1 = lkv[c * 3 + 1], l2 = lkv[c * 3 + 2];\n"
+      << "            const bool male = COL_MALE[c] != 0;\n"
+      << "            const double q0 = __dmul_rn(l0, male ? pm0 : pa0), q1 = __dmul_rn(l1, male ? pm1 : pa1), q2 = __dmul_rn(l2, male ? pm2 : pa2);\n"
+      << "            const double rs = __dadd_rn(__dadd_rn(q0, q1), q2);\n"
+      << "            if (rs <= 0.0) failed = true;\n"
+      << "            gs[c * 3] = __ddiv_rn(q0, rs); gs[c * 3 + 1] = __ddiv_rn(q1, rs); gs[c * 3 + 2] = __ddiv_rn(q2, rs);\n"
+      << "            double big = 0.0;\n"
+      << "            if (big < l0) big = l0;\n"
+      << "            if (big < l1) big = l1;\n"
+      << "            if (big < l2) big = l2;\n"
+      << "            if (__ddiv_rn(big, __dadd_rn(__dadd_rn(l0, l1), l2)) < lrc) pedigree_needed = true;\n"
+      << "        }\n"
+      << "        if (failed) {\n"
+      << "            for (int k = 0; k < NCOL * 3; k++) gp[k] = gs[k] = 0.0;\n"
+      << "            for (int c = 0; c < NCOL; c++) gg[c] = 255;\n"
+      << "            status[v] = 1;\n"
+      << "            continue;\n"
+      << "        }\n"
+      << "        if (!pedigree_needed) { // family.cpp:1973-2058: FPP := individual-only posterior\n"
+      << "            for (int c = 0; c < NCOL; c++) {\n"
+      << "                const double p0 = gs[c * 3], p1 = gs[c * 3 + 1], p2 = gs[c * 3 + 2];\n"
+      << "                gp[c * 3] = p0; gp[c * 3 + 1] = p1; gp[c * 3 + 2] = p2;\n"
+      << "                gg[c] = call_genotype(p0, p1, p2);\n"
+      << "            }\n"
+      << "            status[v] = 0;\n"
+      << "            continue;\n"
+      << "        }\n"
+      << "        const u32 tA = tab_addr, tXF = tab_addr + " << 27 * kRow << "u, tXM = tab_addr + " << 54 * kRow << "u;\n"
+      << "        (void)tA; (void)tXF; (void)tXM;\n"
+      << "        u32 worst = 0u;\n\n"
+      << "        // chain state: own factors (1e6 * prior) * lk for founders, 1e6 * lk otherwise (family.cpp:2115-2126)\n";
+    for (int i = 0; i < n; i++) {
+        const Member &m = M[i];
+        for (int g = 0; g < 3; g++) {
+            std::ostringstream lkx, base;
+            if (m.col >= 0)
+                lkx << "lkv[" << m.col * 3 + g << "]";
+            else
+                lkx << "1.0";
+            if (m.founder)
+                base << "__dmul_rn(1000000.0, " << (m.male ? "pm" : "pa") << g << ")";
+            else
+                base << "1000000.0";
+            const std::string value = "__dmul_rn(" + base.str() + ", " + lkx.str() + ")";
+            if (L.lk_place[i] == GLOB)
+                o << "        *(" << glob_ref(L.lk_row[i], g) << ") = " << value << ";\n";
+            else if (L.lk_place[i] == SMEM)
+                o << "        " << smem_ref(L.lk_row[i], g) << " = " << value << ";\n";
+            else
+                o << "        const double W" << i << "_" << g << " = " << value << ";\n";
+            if (L.acc_place[i] == GLOB)
+                o << "        *(" << glob_ref(L.acc_row[i], g) << ") = 0.0;\n";
+            else if (L.acc_place[i] == SMEM)
+                o << "        " << smem_ref(L.acc_row[i], g) << " = 0.0;\n";
+            else
+                o << "        double A" << i << "_" << g << " = 0.0;\n";
+        }
+    }
+    o << "        const u64 gv = (u64)(v_offset + v);\n"
+      << "        const u32 gv_lo = (u32)gv, gv_hi = (u32)(gv >> 32);\n"
+      << "        u32 r0 = 0, r1 = 0, r2 = 0, r3 = 0;\n"
+      << "        // initial genotypes (family.cpp:2063-2067), stored as table-row byte offsets g * " << kRow << "\n";
+    for (int i = 0; i < n; i++) {
+        if ((i & 3) == 0) o << "        philox(0u, " << (i >> 2) << "u, gv_lo, gv_hi, k0, k1, r0, r1, r2, r3);\n";
+        o << "        u32 o" << i << " = (r" << (i & 3) << " % 3u) * " << kRow << "u;\n";
+    }
+    if (!L.lk_glob.empty()) {
+        const int G = (int)L.lk_glob.size();
+        o << "        // prefetch queue of own factors: " << L.depth << " member(s) ahead\n";
+        for (int j = 0; j < L.depth; j++) {
+            const int row = L.lk_row[L.lk_glob[j % G]];
+            o << "        double q" << j << "_0 = __ldcg(" << glob_ref(row, 0) << "), q" << j << "_1 = __ldcg(" << glob_ref(row, 1) << "), q" << j
+              << "_2 = __ldcg(" << glob_ref(row, 2) << ");\n";
+        }
+    }
+    o << "\n        int sweep = 1;\n"
+      << "        const int last = burn + rep;\n"
+      << "        if (!chrx) {\n"
+      << "        for (; sweep <= burn; sweep++) { // burn-in: no accumulation\n";
+    emit_sweep(o, M, L, false, false, "b");
+    emit_queue_rotation(o, L);
+    o << "        }\n"
+      << "        for (; sweep <= last; sweep++) { // sampling sweeps, Rao-Blackwellised (family.cpp:2175-2178)\n";
+    emit_sweep(o, M, L, true, false, "s");
+    emit_queue_rotation(o, L);
+    o << "        }\n"
+      << "        } else { // the same two loops with the chrX rules\n"
+      << "        for (; sweep <= burn; sweep++) {\n";
+    emit_sweep(o, M, L, false, true, "xb");
+    emit_queue_rotation(o, L);
+    o << "        }\n"
+      << "        for (; sweep <= last; sweep++) {\n";
+    emit_sweep(o, M, L, true, true, "xs");
+    emit_queue_rotation(o, L);
+    o << "        }\n"
+      << "        }\n"
+      << "        if (worst >= 0x78600000u) { status[v] = 2; continue; } // a sum left the fast range: redo with the table-driven kernel\n\n"
+      << "        // postProb = genoFry / numRep, not renormalised; a row summing to <= 0 fails (family.cpp:2082-2092)\n"
+      << "        const double nrep = (double)rep;\n";
+    for (int i = 0; i < n; i++) {
+        o << "        {\n";
+        for (int g = 0; g < 3; g++) {
+            std::string a;
+            if (L.acc_place[i] == GLOB)
+                a = "__ldcg(" + glob_ref(L.acc_row[i], g) + ")";
+            else if (L.acc_place[i] == SMEM)
+                a = smem_ref(L.acc_row[i], g);
+            else
+                a = "A" + std::to_string(i) + "_" + std::to_string(g);
+            o << "            const double p" << g << " = __ddiv_rn(" << a << ", nrep);\n";
+        }
+        o << "            if (__dadd_rn(__dadd_rn(p0, p1), p2) <= 0.0) failed = true;\n";
+        if (M[i].col >= 0) {
+            const int c = M[i].col;
+            o << "            gp[" << c * 3 << "] = p0; gp[" << c * 3 + 1 << "] = p1; gp[" << c * 3 + 2 << "] = p2;\n"
+              << "            gg[" << c << "] = call_genotype(p0, p1, p2);\n";
+        }
+        o << "        }\n";
+    }
+    o << "        if (failed) {\n"
+      << "            for (int k = 0; k < NCOL * 3; k++) gp[k] = gs[k] = 0.0;\n"
+      << "            for (int c = 0; c < NCOL; c++) gg[c] = 255;\n"
+      << "        }\n"
+      << "        status[v] = failed ? 1 : 0;\n"
+      << "    }\n"
+      << "}\n";
+    return o.str();
+}
+
+} // namespace dense
+
+} // namespace
+
+// Which generator: FAMSEQ_JIT_CACHED=0/1 decides; otherwise cached conditionals when at least three quarters of the
+// members are sequenced (unsequenced members have flat likelihoods: their genotypes, and with them their neighbours'
+// conditionals, change all the time, and a cache that is always stale only costs).
+GibbsJitConfig gibbs_jit_default_config(const McmcParams &P) {
+    int sequenced = 0;
+    for (int i = 0; i < P.plan.n; i++) sequenced += P.plan.col[i] >= 0;
+    const int want = env_int("FAMSEQ_JIT_CACHED", 4 * sequenced >= 3 * P.plan.n ? 1 : 0);
+    return want ? cached::default_config(P) : dense::default_config(P);
+}
+
+std::string gibbs_jit_source(const McmcParams &P, const GibbsJitConfig &cfg) { return cfg.cached ? cached::source(P, cfg) : dense::source(P, cfg); }
+
+namespace {
+// shared memory and block-private scratch (doubles per block) of a layout
+size_t layout_smem(const McmcParams &P, const GibbsJitConfig &cfg) {
+    return cfg.cached ? cached::smem_bytes(cached::make_layout(P.plan.n, cfg), cfg.tb) : dense::smem_bytes(dense::make_layout(P.plan.n, cfg), cfg.tb);
+}
+size_t layout_scratch_doubles(const McmcParams &P, const GibbsJitConfig &cfg) {
+    if (cfg.cached) return (size_t)P.plan.n * cached::kScratchRows * cfg.tb;
+    return (size_t)std::max(1, dense::make_layout(P.plan.n, cfg).glob_rows) * 3 * cfg.tb;
+}
+} // namespace
+
 // ---- NVRTC, bound at run time so that the engine library itself has no link-time dependency on it ---------------
 namespace {
 
@@ -662,18 +1087,17 @@ struct GibbsJitKernel {
     cudaKernel_t kernel = nullptr;
     GibbsJitConfig cfg;
     size_t smem = 0;
-    int glob_rows = 0;
+    size_t scratch_doubles = 0; // block-private scratch, doubles per block
     int blocks_per_sm = 1;
 };
 
 int gibbs_jit_load(const McmcParams &P, const GibbsJitConfig &cfg, const std::string &cubin, GibbsJitKernel **out, std::string &err) {
     *out = nullptr;
-    const Layout L = make_layout(P.plan.n, cfg);
-    const size_t smem = smem_bytes(L, cfg.tb);
+    const size_t smem = layout_smem(P, cfg);
     GibbsJitKernel *k = new GibbsJitKernel();
     k->cfg = cfg;
     k->smem = smem;
-    k->glob_rows = L.n * kScratchRows;
+    k->scratch_doubles = layout_scratch_doubles(P, cfg);
     auto cuda_err = [&](cudaError_t e, const char *what) {
         err = std::string("Gibbs JIT: ") + what + ": " + cudaGetErrorString(e);
         gibbs_jit_unload(k);
@@ -695,8 +1119,7 @@ int gibbs_jit_load(const McmcParams &P, const GibbsJitConfig &cfg, const std::st
 }
 
 int gibbs_jit_build(const McmcParams &P, const GibbsJitConfig &cfg, std::string &cubin, std::string &log, std::string &err) {
-    const Layout L = make_layout(P.plan.n, cfg);
-    const size_t smem = smem_bytes(L, cfg.tb);
+    const size_t smem = layout_smem(P, cfg);
     if (cfg.tb < 32 || cfg.tb > 1024 || cfg.tb % 32 || smem > kSmemPerBlockMax) {
         err = "Gibbs JIT: invalid layout (tb " + std::to_string(cfg.tb) + ", shared memory " + std::to_string(smem) + " B)";
         return FS_E_TOO_LARGE;
@@ -705,8 +1128,8 @@ int gibbs_jit_build(const McmcParams &P, const GibbsJitConfig &cfg, std::string 
     if (rc != FS_OK) return rc;
     if (const char *v = std::getenv("FAMSEQ_JIT_VERBOSE"))
         if (v[0] == '1')
-            std::fprintf(stderr, "[famseq] Gibbs JIT tb=%d blocks=%d draw thresholds of %d members in registers, smem=%zu\n%s\n", cfg.tb,
-                         cfg.blocks, cfg.n_p_reg, smem, log.c_str());
+            std::fprintf(stderr, "[famseq] Gibbs JIT (%s) tb=%d blocks=%d smem=%zu\n%s\n", cfg.cached ? "cached conditionals" : "dense sweeps", cfg.tb,
+                         cfg.blocks, smem, log.c_str());
     return FS_OK;
 }
 
@@ -725,7 +1148,7 @@ cudaError_t gibbs_jit_launch(GibbsJitKernel *k, const BatchPtrs &B, int burn, in
     int n_tiles = (int)n_tiles64;
     const int grid = (int)std::min<int64_t>(n_tiles64, (int64_t)sm_count * k->blocks_per_sm);
     double *scratch = nullptr; // accumulators and run bookkeeping [grid][member][6][tb], stream-ordered
-    cudaError_t rc = cudaMallocAsync(&scratch, (size_t)grid * std::max(1, k->glob_rows) * tb * sizeof(double), stream);
+    cudaError_t rc = cudaMallocAsync(&scratch, (size_t)grid * std::max<size_t>(1, k->scratch_doubles) * sizeof(double), stream);
     if (rc != cudaSuccess) return rc;
     const double *lk = B.lk;
     const uint8_t *flags = B.flags;

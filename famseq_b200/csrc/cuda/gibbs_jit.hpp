@@ -14,12 +14,18 @@ namespace famseq {
 // draw thresholds: for the first n_p_reg members in registers, for the others in thread-private shared-memory columns
 // (see gibbs_jit.cu).
 struct GibbsJitConfig {
+    int cached = 1;  // 1: cached conditionals + integer draws (generator 1), 0: dense sweeps (generator 2, round 1's kernel)
     int tb = 0;      // chains (threads) per block
     int blocks = 1;  // resident blocks per SM the register budget is sized for
-    int n_p_reg = 0; // members whose thresholds live in registers
+    int n_p_reg = 0; // cached: members whose thresholds live in registers
+    // dense: per chain 3 own factors and 3 accumulators per member, placed in ped order: the first n_*_reg in registers, the
+    // next n_*_smem in shared memory, the rest in a block-private global scratch (L2)
+    int n_acc_reg = 0, n_acc_smem = 0;
+    int n_lk_reg = 0, n_lk_smem = 0;
+    int prefetch = 1; // dense: own factors read from the scratch are requested this many members ahead
 };
 
-// Layout heuristic (overridable with FAMSEQ_JIT_TB / _BLOCKS / _PREG).
+// Layout heuristic (FAMSEQ_JIT_CACHED=0/1 picks the generator; FAMSEQ_JIT_TB / _BLOCKS, cached: _PREG, dense: _RACC / _SACC / _RLK / _SLK / _PF).
 GibbsJitConfig gibbs_jit_default_config(const McmcParams &P);
 
 std::string gibbs_jit_source(const McmcParams &P, const GibbsJitConfig &cfg);
