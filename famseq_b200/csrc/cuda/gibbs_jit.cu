@@ -355,7 +355,7 @@ void emit_sweep(std::ostringstream &o, const std::vector<Member> &M, const Layou
         o << "                        done = true;\n                    }\n                }\n"
           << "                if (__builtin_expect(!done, 0)) { // member by member, in the reference's order\n";
         for (int i = a; i < b; i++) emit_member_serial(o, M, L, nb, i, chrx, u_of(i));
-        o << "                }\n            }\n";
+        o << "                }\n                __syncwarp(live);\n            }\n";
     }
 }
 
@@ -423,6 +423,8 @@ std::string source(const McmcParams &P, const GibbsJitConfig &cfg) {
       << "    (void)st; (void)wg;\n\n"
       << "    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {\n"
       << "        const i64 v = (i64)tile * TB + tid;\n"
+      << "        __syncwarp(); // every lane of every warp runs the same tiles: start each one converged\n"
+      << "        const u32 in_tile = __ballot_sync(0xffffffffu, v < V);\n"
       << "        if (v >= V) continue;\n"
       << "        const u32 flag = flags ? flags[v] : 0u;\n"
       << "        const bool known = flag & 1u, chrx = (flag >> 1) & 1u;\n"
@@ -453,17 +455,19 @@ std::string source(const McmcParams &P, const GibbsJitConfig &cfg) {
       << "            for (int k = 0; k < NCOL * 3; k++) gp[k] = gs[k] = 0.0;\n"
       << "            for (int c = 0; c < NCOL; c++) gg[c] = 255;\n"
       << "            status[v] = 1;\n"
-      << "            continue;\n"
-      << "        }\n"
-      << "        if (!pedigree_needed) { // family.cpp:1973-2058: FPP := individual-only posterior\n"
+      << "        } else if (!pedigree_needed) { // family.cpp:1973-2058: FPP := individual-only posterior\n"
       << "            for (int c = 0; c < NCOL; c++) {\n"
       << "                const double p0 = gs[c * 3], p1 = gs[c * 3 + 1], p2 = gs[c * 3 + 2];\n"
       << "                gp[c * 3] = p0; gp[c * 3 + 1] = p1; gp[c * 3 + 2] = p2;\n"
       << "                gg[c] = call_genotype(p0, p1, p2);\n"
       << "            }\n"
       << "            status[v] = 0;\n"
-      << "            continue;\n"
       << "        }\n"
+      << "        // the lanes that go on to sample: the sweeps re-converge them after every group (a group redone member by\n"
+      << "        // member leaves its lanes behind; left alone, the warp falls apart into single lanes for the rest of the run)\n"
+      << "        const bool sampling = !failed && pedigree_needed;\n"
+      << "        const u32 live = __ballot_sync(in_tile, sampling);\n"
+      << "        if (!sampling) continue;\n"
       << "        const u32 tA = tab_addr, tXF = tab_addr + " << 27 * kRow << "u, tXM = tab_addr + " << 54 * kRow << "u;\n"
       << "        (void)tA; (void)tXF; (void)tXM;\n"
       << "        u32 worst = 0u;\n\n"
