@@ -307,7 +307,11 @@ void emit_member_serial(std::ostringstream &o, const std::vector<Member> &M, con
     o << "                  o" << i << " = g; }\n";
 }
 
-// One sweep: groups of kGroup members, each drawn side by side when it can be, member by member when it must be.
+// One sweep: groups of kGroup members, each drawn side by side when it can be, member by member when it must be.  The choice
+// is made per WARP (a vote): control flow stays uniform, so the lanes of a warp never drift apart (with a per-lane branch the
+// rare member-by-member lanes were left behind for good and the warp degenerated into single lanes: 20 times the
+// instructions, profiles/r2e_r2e_mcmc.txt).  For a lane whose own group was fine, the member-by-member path evaluates nothing
+// and draws the same genotypes from the same thresholds and random words.
 void emit_sweep(std::ostringstream &o, const std::vector<Member> &M, const Layout &L, const std::vector<std::vector<int>> &nb, bool chrx) {
     const int n = (int)M.size(), words = (n + 31) / 32;
     for (int a = 0; a < n; a += kGroup) {
@@ -324,38 +328,30 @@ void emit_sweep(std::ostringstream &o, const std::vector<Member> &M, const Layou
                   << "_3);\n";
             }
         auto u_of = [](int i) { return "(x" + std::to_string(i >> 2) + "_" + std::to_string(i & 3) + " >> 1)"; };
-        o << "                bool done = false;\n"
-          << "                if (__builtin_expect((D" << w << " & " << gmask << "u) == 0u, 1)) { // nobody dirty: draw the group side by side\n";
+        // the draws of the group, side by side, from the cached thresholds (only used if the group turns out to be clean)
         for (int i = a; i < b; i++)
-            o << "                    const u32 g" << i << " = (" << u_of(i) << " < " << t0_ref(L, i) << ") ? 0u : ((" << u_of(i) << " >= " << t2_ref(L, i) << ") ? "
+            o << "                const u32 g" << i << " = (" << u_of(i) << " < " << t0_ref(L, i) << ") ? 0u : ((" << u_of(i) << " >= " << t2_ref(L, i) << ") ? "
               << 2 * kRow << "u : " << kRow << "u);\n";
+        std::vector<bool> word_used(words, false);
         for (int ww = 0; ww < words; ww++) {
-            bool any = false;
-            for (int i = a; i < b; i++) any = any || neighbour_mask(nb, i, words)[ww];
-            if (!any) continue;
-            o << "                    const u32 n" << ww << " = 0u";
+            for (int i = a; i < b; i++) word_used[ww] = word_used[ww] || neighbour_mask(nb, i, words)[ww];
+            if (!word_used[ww]) continue;
+            o << "                const u32 n" << ww << " = 0u";
             for (int i = a; i < b; i++) {
                 const unsigned mk = neighbour_mask(nb, i, words)[ww];
                 if (mk) o << " | ((g" << i << " != o" << i << ") ? " << mk << "u : 0u)";
             }
             o << ";\n";
         }
-        bool own_word = false;
-        for (int i = a; i < b; i++) own_word = own_word || neighbour_mask(nb, i, words)[w];
-        if (own_word)
-            o << "                    if (__builtin_expect((n" << w << " & " << gmask << "u) == 0u, 1)) { // no change next to a group mate: commit\n";
-        else
-            o << "                    {\n";
-        for (int i = a; i < b; i++) o << "                        o" << i << " = g" << i << ";\n";
-        for (int ww = 0; ww < words; ww++) {
-            bool any = false;
-            for (int i = a; i < b; i++) any = any || neighbour_mask(nb, i, words)[ww];
-            if (any) o << "                        D" << ww << " |= n" << ww << ";\n";
-        }
-        o << "                        done = true;\n                    }\n                }\n"
-          << "                if (__builtin_expect(!done, 0)) { // member by member, in the reference's order\n";
+        // fine for this lane: nobody in the group is dirty, and no member that changes has a neighbour inside the group
+        o << "                const bool fine = ((D" << w << (word_used[w] ? " | n" + std::to_string(w) : std::string()) << ") & " << gmask << "u) == 0u;\n"
+          << "                if (__all_sync(live, fine)) { // commit\n";
+        for (int i = a; i < b; i++) o << "                    o" << i << " = g" << i << ";\n";
+        for (int ww = 0; ww < words; ww++)
+            if (word_used[ww]) o << "                    D" << ww << " |= n" << ww << ";\n";
+        o << "                } else { // member by member, in the reference's order\n";
         for (int i = a; i < b; i++) emit_member_serial(o, M, L, nb, i, chrx, u_of(i));
-        o << "                }\n                __syncwarp(live);\n            }\n";
+        o << "                }\n            }\n";
     }
 }
 
@@ -463,11 +459,13 @@ std::string source(const McmcParams &P, const GibbsJitConfig &cfg) {
       << "            }\n"
       << "            status[v] = 0;\n"
       << "        }\n"
-      << "        // the lanes that go on to sample: the sweeps re-converge them after every group (a group redone member by\n"
-      << "        // member leaves its lanes behind; left alone, the warp falls apart into single lanes for the rest of the run)\n"
+      << "        // the lanes that go on to sample (the mask of the per-group votes in the sweeps)\n"
       << "        const bool sampling = !failed && pedigree_needed;\n"
-      << "        const u32 live = __ballot_sync(in_tile, sampling);\n"
+      << "        const u32 sampling_lanes = __ballot_sync(in_tile, sampling);\n"
       << "        if (!sampling) continue;\n"
+      << "        // autosomal and chrX variants of a warp run different loops: each loop votes among its own lanes\n"
+      << "        const u32 autosomal_lanes = __ballot_sync(sampling_lanes, !chrx);\n"
+      << "        const u32 live = chrx ? (sampling_lanes & ~autosomal_lanes) : autosomal_lanes;\n"
       << "        const u32 tA = tab_addr, tXF = tab_addr + " << 27 * kRow << "u, tXM = tab_addr + " << 54 * kRow << "u;\n"
       << "        (void)tA; (void)tXF; (void)tXM;\n"
       << "        u32 worst = 0u;\n\n"

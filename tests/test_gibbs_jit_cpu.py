@@ -35,6 +35,7 @@ static unsigned char smem_raw[232448] __attribute__((aligned(128)));
 static inline void __syncthreads() {}
 static inline void __syncwarp(unsigned = 0xffffffffu) {}
 static inline unsigned __ballot_sync(unsigned, bool p) { return p ? 1u : 0u; }
+static inline bool __all_sync(unsigned, bool p) { return p; }
 static inline size_t __cvta_generic_to_shared(const void *p) { return (size_t)((const unsigned char *)p - smem_raw); }
 static inline double lds64(u32 a) { double v; std::memcpy(&v, smem_raw + a, 8); return v; }
 static inline double __ldcg(const double *p) { return *p; }
