@@ -97,13 +97,21 @@ struct EsJitState {
     std::thread worker;
     EsJitKernel *kernel = nullptr;
 };
+// Two generators (gibbs_jit.cu): [1] cached conditionals, fast where the chains sit still; [0] dense sweeps, whose speed does
+// not depend on the data.  `pick` is the generator in use: it starts as the static choice of gibbs_jit_default_config and,
+// unless FAMSEQ_JIT_CACHED fixes it, is settled by a pilot on the first large batch that is about to run the cached kernel:
+// 256 sweeps over the first few thousand variants, counting how many groups the warps had to redo member by member.
 struct GibbsJitState {
     int mode = 2;
     double min_work = 2e10; // Gibbs steps (variants x sweeps x members) seen by this engine before a compile is started
     double work_seen = 0;
-    std::shared_ptr<GibbsJitJob> job;
-    std::thread worker;
-    GibbsJitKernel *kernel = nullptr;
+    std::shared_ptr<GibbsJitJob> job[2];
+    std::thread worker[2];
+    GibbsJitKernel *kernel[2] = {nullptr, nullptr};
+    int pick = -1;
+    bool piloted = false;
+    double pilot_serial_fraction = -1; // what the pilot measured (fs_get_info reports the generator)
+    unsigned long long *d_vote_stats = nullptr;
 };
 } // namespace
 
@@ -145,6 +153,7 @@ struct fs_engine {
 
     DeviceChunk chunk[kPipelineDepth];
     int64_t launches = 0, jit_launches = 0;
+    int gibbs_generator = 0; // generated Gibbs kernel of the last MCMC launch: 0 none (table-driven), 1 dense sweeps, 2 cached conditionals
     double last_kernel_ms = 0;
 
     std::vector<fs_engine *> parts; // fs_create_multi: one single-device engine per GPU (this one then has device -1)
@@ -202,12 +211,13 @@ static void release_chunks(fs_engine *e) {
 void fs_destroy(fs_engine *e) {
     if (!e) return;
     for (fs_engine *part : e->parts) fs_destroy(part);
-    if (e->jit.worker.joinable()) { // do not wait for a compile nobody will use
-        if (e->jit.job && e->jit.job->state.load(std::memory_order_acquire) == GibbsJitJob::COMPILING)
-            e->jit.worker.detach();
-        else
-            e->jit.worker.join();
-    }
+    for (int g = 0; g < 2; g++)
+        if (e->jit.worker[g].joinable()) { // do not wait for a compile nobody will use
+            if (e->jit.job[g] && e->jit.job[g]->state.load(std::memory_order_acquire) == GibbsJitJob::COMPILING)
+                e->jit.worker[g].detach();
+            else
+                e->jit.worker[g].join();
+        }
     if (e->es_jit.worker.joinable()) {
         if (e->es_jit.job && e->es_jit.job->state.load(std::memory_order_acquire) == EsJitJob::COMPILING)
             e->es_jit.worker.detach();
@@ -216,7 +226,9 @@ void fs_destroy(fs_engine *e) {
     }
     if (e->device >= 0) {
         cudaSetDevice(e->device);
-        gibbs_jit_unload(e->jit.kernel);
+        gibbs_jit_unload(e->jit.kernel[0]);
+        gibbs_jit_unload(e->jit.kernel[1]);
+        cudaFree(e->jit.d_vote_stats);
         es_jit_unload(e->es_jit.kernel);
         release_chunks(e);
         cudaFree(e->d_pl_table);
@@ -408,6 +420,7 @@ int fs_get_info(const fs_engine *e, fs_info *out) {
     out->kernel_launches = e->launches;
     out->jit_launches = e->jit_launches;
     out->n_devices = e->parts.empty() ? (e->device >= 0 ? 1 : 0) : (int32_t)e->parts.size();
+    out->gibbs_generator = e->parts.empty() ? e->gibbs_generator : e->parts[0]->gibbs_generator;
     for (const fs_engine *part : e->parts) {
         fs_info pi;
         const int rc = fs_get_info(part, &pi);
@@ -514,19 +527,19 @@ void fs_free_pinned(void *p) {
 
 double fs_last_kernel_ms(const fs_engine *e) { return e ? e->last_kernel_ms : 0.0; }
 
-// The specialised Gibbs kernel if it is ready (loads it when the worker has finished, starts the worker when this
+// The Gibbs kernel of generator `which` if it is ready (loads it when the worker has finished, starts the worker when this
 // batch is big enough); nullptr means: use the table-driven kernel for this batch.
-static int gibbs_jit_poll(fs_engine *e, double work, GibbsJitKernel **out) {
+static int gibbs_jit_poll(fs_engine *e, double work, int which, GibbsJitKernel **out) {
     GibbsJitState &J = e->jit;
     *out = nullptr;
     if (J.mode == 0) return FS_OK;
     J.work_seen += work;
-    if (!J.job && (J.mode == 1 || J.work_seen >= J.min_work)) {
-        J.job = std::make_shared<GibbsJitJob>();
-        J.job->params = e->mcmc;
-        J.job->cfg = gibbs_jit_default_config(e->mcmc);
-        J.job->state.store(GibbsJitJob::COMPILING, std::memory_order_release);
-        std::shared_ptr<GibbsJitJob> job = J.job;
+    if (!J.job[which] && (J.mode == 1 || J.work_seen >= J.min_work)) {
+        J.job[which] = std::make_shared<GibbsJitJob>();
+        J.job[which]->params = e->mcmc;
+        J.job[which]->cfg = gibbs_jit_config(e->mcmc, which);
+        J.job[which]->state.store(GibbsJitJob::COMPILING, std::memory_order_release);
+        std::shared_ptr<GibbsJitJob> job = J.job[which];
         auto build = [job]() {
             const int rc = gibbs_jit_build(job->params, job->cfg, job->cubin, job->log, job->err);
             job->state.store(rc == FS_OK ? GibbsJitJob::COMPILED : GibbsJitJob::FAILED, std::memory_order_release);
@@ -534,20 +547,53 @@ static int gibbs_jit_poll(fs_engine *e, double work, GibbsJitKernel **out) {
         if (J.mode == 1)
             build();
         else
-            J.worker = std::thread(build);
+            J.worker[which] = std::thread(build);
     }
-    if (!J.job) return FS_OK;
-    int st = J.job->state.load(std::memory_order_acquire);
+    if (!J.job[which]) return FS_OK;
+    int st = J.job[which]->state.load(std::memory_order_acquire);
     if (st == GibbsJitJob::COMPILED) {
-        if (J.worker.joinable()) J.worker.join();
-        const int rc = gibbs_jit_load(e->mcmc, J.job->cfg, J.job->cubin, &J.kernel, J.job->err);
-        J.job->cubin.clear();
-        J.job->cubin.shrink_to_fit();
+        if (J.worker[which].joinable()) J.worker[which].join();
+        const int rc = gibbs_jit_load(e->mcmc, J.job[which]->cfg, J.job[which]->cubin, &J.kernel[which], J.job[which]->err);
+        J.job[which]->cubin.clear();
+        J.job[which]->cubin.shrink_to_fit();
         st = rc == FS_OK ? GibbsJitJob::LOADED : GibbsJitJob::FAILED;
-        J.job->state.store(st, std::memory_order_release);
+        J.job[which]->state.store(st, std::memory_order_release);
     }
-    if (st == GibbsJitJob::FAILED && J.mode == 1) return fail(FS_E_CUDA, "FAMSEQ_MCMC_JIT=1: " + J.job->err);
-    if (st == GibbsJitJob::LOADED) *out = J.kernel;
+    if (st == GibbsJitJob::FAILED && J.mode == 1) return fail(FS_E_CUDA, "FAMSEQ_MCMC_JIT=1: " + J.job[which]->err);
+    if (st == GibbsJitJob::LOADED) *out = J.kernel[which];
+    return FS_OK;
+}
+
+// The pilot: the cached kernel on the head of the batch for 192 + 64 sweeps into throw-away outputs; *fraction receives the
+// share of groups its warps redid member by member during the 64 sampling sweeps.  Synchronises the stream (once per engine).
+static int gibbs_pilot(fs_engine *e, GibbsJitKernel *jk, const BatchPtrs &B, uint64_t seed, int64_t v_offset, cudaStream_t stream,
+                       double *fraction) {
+    GibbsJitState &J = e->jit;
+    const int64_t n = std::min<int64_t>(B.V, 8192);
+    const size_t S = (size_t)e->ped.s(), nd = std::max<size_t>((size_t)n * S * 3, 2) * sizeof(double);
+    if (!J.d_vote_stats) FS_CUDA(cudaMalloc(&J.d_vote_stats, 2 * sizeof(unsigned long long)));
+    double *post = nullptr, *single = nullptr;
+    uint8_t *gt = nullptr, *status = nullptr;
+    auto release = [&]() {
+        cudaFree(post);
+        cudaFree(single);
+        cudaFree(gt);
+        cudaFree(status);
+    };
+    cudaError_t rc = cudaMalloc(&post, nd);
+    if (rc == cudaSuccess) rc = cudaMalloc(&single, nd);
+    if (rc == cudaSuccess) rc = cudaMalloc(&gt, std::max<size_t>((size_t)n * S, 16));
+    if (rc == cudaSuccess) rc = cudaMalloc(&status, (size_t)n);
+    if (rc == cudaSuccess) rc = cudaMemsetAsync(J.d_vote_stats, 0, 2 * sizeof(unsigned long long), stream);
+    BatchPtrs P{B.lk, B.flags, post, single, gt, status, n};
+    if (rc == cudaSuccess) rc = gibbs_jit_launch(jk, P, 192, 64, seed, v_offset, e->sm_count, stream, J.d_vote_stats);
+    unsigned long long stats[2] = {0, 0};
+    if (rc == cudaSuccess) rc = cudaMemcpyAsync(stats, J.d_vote_stats, sizeof stats, cudaMemcpyDeviceToHost, stream);
+    if (rc == cudaSuccess) rc = cudaStreamSynchronize(stream);
+    release();
+    if (rc != cudaSuccess) return cuda_fail(rc, "Gibbs pilot");
+    e->launches++;
+    *fraction = stats[1] ? (double)stats[0] / (double)stats[1] : 0.0;
     return FS_OK;
 }
 
@@ -672,9 +718,24 @@ static int dispatch(fs_engine *e, int method, BatchPtrs B, int32_t burn, int32_t
         krc = launch_bn(e->bn, B, e->sm_count, stream);
         break;
     case FS_METHOD_MCMC: {
+        GibbsJitState &J = e->jit;
+        if (J.pick < 0) J.pick = gibbs_jit_default_config(e->mcmc).cached;
         GibbsJitKernel *jk = nullptr;
-        frc = gibbs_jit_poll(e, (double)B.V * ((double)burn + rep) * e->ped.n, &jk);
+        const double work = (double)B.V * ((double)burn + rep) * e->ped.n;
+        frc = gibbs_jit_poll(e, work, J.pick, &jk);
         if (frc != FS_OK) break;
+        if (jk && J.pick == 1 && !J.piloted && !gibbs_jit_generator_forced() && B.V >= 2048 && (int64_t)burn + rep >= 1024) {
+            // is this the data the cached kernel is made for?  (where the chains keep moving -- low coverage, Mendelian
+            // inconsistencies -- its cache is always stale and the dense generator is ~8x faster)
+            J.piloted = true;
+            frc = gibbs_pilot(e, jk, B, seed, v_offset, stream, &J.pilot_serial_fraction);
+            if (frc != FS_OK) break;
+            if (J.pilot_serial_fraction > 0.4) {
+                J.pick = 0;
+                frc = gibbs_jit_poll(e, 0.0, 0, &jk);
+                if (frc != FS_OK) break;
+            }
+        }
         if (jk) {
             // the specialised kernel covers chains whose weight sums stay positive normal numbers away from the exponent
             // limits; it marks the others with status 2 for a second pass of the table-driven kernel (counted in d_fixups)
@@ -688,6 +749,7 @@ static int dispatch(fs_engine *e, int method, BatchPtrs B, int32_t burn, int32_t
                 krc = launch_mcmc(e->mcmc, B, e->mcmc_tb, burn, rep, seed, v_offset, e->sm_count, stream, e->mcmc_tune, true, e->d_fixups);
             e->jit_launches++;
             e->launches++;
+            e->gibbs_generator = 1 + J.pick;
         } else
             krc = launch_mcmc(e->mcmc, B, e->mcmc_tb, burn, rep, seed, v_offset, e->sm_count, stream, e->mcmc_tune);
         break;

@@ -349,7 +349,8 @@ void emit_sweep(std::ostringstream &o, const std::vector<Member> &M, const Layou
         for (int i = a; i < b; i++) o << "                    o" << i << " = g" << i << ";\n";
         for (int ww = 0; ww < words; ww++)
             if (word_used[ww]) o << "                    D" << ww << " |= n" << ww << ";\n";
-        o << "                } else { // member by member, in the reference's order\n";
+        o << "                } else { // member by member, in the reference's order\n"
+          << "                    n_serial += sweep > burn ? 1u : 0u;\n";
         for (int i = a; i < b; i++) emit_member_serial(o, M, L, nb, i, chrx, u_of(i));
         o << "                }\n            }\n";
     }
@@ -403,7 +404,7 @@ std::string source(const McmcParams &P, const GibbsJitConfig &cfg) {
     o << "\nextern \"C\" __global__ void __launch_bounds__(TB, " << cfg.blocks << ")\n"
       << "famseq_gibbs(const double *__restrict__ lk, const u8 *__restrict__ flags, double *__restrict__ post,\n"
       << "             double *__restrict__ single, u8 *__restrict__ gt, u8 *__restrict__ status, i64 V, int burn, int rep,\n"
-      << "             u64 seed, i64 v_offset, double *scratch, int n_tiles) {\n"
+      << "             u64 seed, i64 v_offset, double *scratch, int n_tiles, u64 *vote_stats) {\n"
       << "    extern __shared__ __align__(16) unsigned char smem_raw[];\n"
       << "    double *s_tab = (double *)smem_raw;              // [81][" << kCopies << "]\n"
       << "    u32 *s_thr = (u32 *)(s_tab + 81 * " << kCopies << ");    // [" << L.smem_pairs << " * 2][TB] thread-private columns: T0, T2\n"
@@ -492,6 +493,7 @@ std::string source(const McmcParams &P, const GibbsJitConfig &cfg) {
     o << "\n        const int last = burn + rep;\n"
       << "        const double first = (double)(burn + 1); // first sampling sweep: runs are counted from here (family.cpp:2069-2080)\n"
       << "        double tD = 1.0;                          // the sweep index as a double\n"
+      << "        u32 n_serial = 0u;                        // groups of the sampling sweeps this warp redid member by member\n"
       << "        if (!chrx) {\n"
       << "        for (int sweep = 1; sweep <= last; sweep++, tD = __dadd_rn(tD, 1.0)) {\n";
     emit_sweep(o, M, L, nb, false);
@@ -500,6 +502,10 @@ std::string source(const McmcParams &P, const GibbsJitConfig &cfg) {
       << "        for (int sweep = 1; sweep <= last; sweep++, tD = __dadd_rn(tD, 1.0)) {\n";
     emit_sweep(o, M, L, nb, true);
     o << "        }\n"
+      << "        }\n"
+      << "        if (vote_stats && (live & (live - 1u)) == (live ^ (1u << lane))) { // the lowest live lane reports for the warp\n"
+      << "            atomicAdd(vote_stats, (u64)n_serial);\n"
+      << "            atomicAdd(vote_stats + 1, (u64)rep * " << (n + kGroup - 1) / kGroup << "ull);\n"
       << "        }\n"
       << "        if (worst >= 0x78600000u) { status[v] = 2; continue; } // a sum left the fast range: redo with the table-driven kernel\n\n"
       << "        // postProb = genoFry / numRep, not renormalised; a row summing to <= 0 fails (family.cpp:2082-2092).\n"
@@ -767,7 +773,7 @@ std::string source(const McmcParams &P, const GibbsJitConfig &cfg) {
     o << "\nextern \"C\" __global__ void __launch_bounds__(TB, " << cfg.blocks << ")\n"
       << "famseq_gibbs(const double *__restrict__ lk, const u8 *__restrict__ flags, double *__restrict__ post,\n"
       << "             double *__restrict__ single, u8 *__restrict__ gt, u8 *__restrict__ status, i64 V, int burn, int rep,\n"
-      << "             u64 seed, i64 v_offset, double *scratch, int n_tiles) {\n"
+      << "             u64 seed, i64 v_offset, double *scratch, int n_tiles, u64 *vote_stats) {\n"
       << "    extern __shared__ __align__(16) unsigned char smem_raw[];\n"
       << "    double *s_tab = (double *)smem_raw;              // [81][" << kCopies << "]\n"
       << "    double *s_vec = s_tab + 81 * " << kCopies << ";           // [" << L.smem_rows << " * 3][TB] thread-private columns\n"
@@ -780,7 +786,7 @@ std::string source(const McmcParams &P, const GibbsJitConfig &cfg) {
       << "    double *wg = scratch + (size_t)blockIdx.x * " << std::max(1, L.glob_rows) * 3 << " * TB + tid; // [row][g][TB], block-private\n"
       << "    const u32 k0 = (u32)seed, k1 = (u32)(seed >> 32);\n"
       << "    const double lrc = __longlong_as_double((i64)" << bits(C.lrc) << ");\n"
-      << "    (void)sa; (void)wg;\n\n"
+      << "    (void)sa; (void)wg; (void)vote_stats;\n\n"
       << "    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {\n"
       << "        const i64 v = (i64)tile * TB + tid;\n"
       << "        if (v >= V) continue;\n"
@@ -938,6 +944,13 @@ GibbsJitConfig gibbs_jit_default_config(const McmcParams &P) {
     for (int i = 0; i < P.plan.n; i++) sequenced += P.plan.col[i] >= 0;
     const int want = env_int("FAMSEQ_JIT_CACHED", 4 * sequenced >= 3 * P.plan.n ? 1 : 0);
     return want ? cached::default_config(P) : dense::default_config(P);
+}
+
+GibbsJitConfig gibbs_jit_config(const McmcParams &P, int cached) { return cached ? cached::default_config(P) : dense::default_config(P); }
+
+bool gibbs_jit_generator_forced() {
+    const char *v = std::getenv("FAMSEQ_JIT_CACHED");
+    return v && *v;
 }
 
 std::string gibbs_jit_source(const McmcParams &P, const GibbsJitConfig &cfg) { return cfg.cached ? cached::source(P, cfg) : dense::source(P, cfg); }
@@ -1142,7 +1155,7 @@ void gibbs_jit_unload(GibbsJitKernel *k) {
 }
 
 cudaError_t gibbs_jit_launch(GibbsJitKernel *k, const BatchPtrs &B, int burn, int rep, uint64_t seed, int64_t v_offset,
-                             int sm_count, cudaStream_t stream) {
+                             int sm_count, cudaStream_t stream, unsigned long long *vote_stats) {
     if (B.V <= 0) return cudaSuccess;
     const int tb = k->cfg.tb;
     const int64_t n_tiles64 = (B.V + tb - 1) / tb;
@@ -1158,7 +1171,7 @@ cudaError_t gibbs_jit_launch(GibbsJitKernel *k, const BatchPtrs &B, int burn, in
     uint8_t *gt = B.gt, *status = B.status;
     long long V = B.V, voff = v_offset;
     unsigned long long sd = seed;
-    void *args[] = {&lk, &flags, &post, &single, &gt, &status, &V, &burn, &rep, &sd, &voff, &scratch, &n_tiles};
+    void *args[] = {&lk, &flags, &post, &single, &gt, &status, &V, &burn, &rep, &sd, &voff, &scratch, &n_tiles, &vote_stats};
     rc = cudaLaunchKernel((const void *)k->kernel, dim3(grid), dim3(tb), args, k->smem, stream);
     const cudaError_t rc2 = cudaFreeAsync(scratch, stream);
     return rc != cudaSuccess ? rc : rc2;

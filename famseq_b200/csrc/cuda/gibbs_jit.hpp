@@ -27,6 +27,8 @@ struct GibbsJitConfig {
 
 // Layout heuristic (FAMSEQ_JIT_CACHED=0/1 picks the generator; FAMSEQ_JIT_TB / _BLOCKS, cached: _PREG, dense: _RACC / _SACC / _RLK / _SLK / _PF).
 GibbsJitConfig gibbs_jit_default_config(const McmcParams &P);
+GibbsJitConfig gibbs_jit_config(const McmcParams &P, int cached); // the layout of one generator
+bool gibbs_jit_generator_forced();                                // FAMSEQ_JIT_CACHED is set: no pilot, no switching
 
 std::string gibbs_jit_source(const McmcParams &P, const GibbsJitConfig &cfg);
 
@@ -39,7 +41,8 @@ int gibbs_jit_build(const McmcParams &P, const GibbsJitConfig &cfg, std::string 
 struct GibbsJitKernel; // a loaded cubin
 int gibbs_jit_load(const McmcParams &P, const GibbsJitConfig &cfg, const std::string &cubin, GibbsJitKernel **out, std::string &err);
 void gibbs_jit_unload(GibbsJitKernel *k);
+// vote_stats (device, may be null): the cached generator adds {groups redone member by member, groups} of the sampling sweeps
 cudaError_t gibbs_jit_launch(GibbsJitKernel *k, const BatchPtrs &B, int burn, int rep, uint64_t seed, int64_t v_offset,
-                             int sm_count, cudaStream_t stream);
+                             int sm_count, cudaStream_t stream, unsigned long long *vote_stats = nullptr);
 
 } // namespace famseq

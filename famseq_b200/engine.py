@@ -63,7 +63,7 @@ class _Info(ctypes.Structure):
                                                                                       ("jit_launches", ctypes.c_int64),
                                                                                       ("mcmc_fixups", ctypes.c_int64),
                                                                                       ("n_devices", ctypes.c_int32),
-                                                                                      ("reserved", ctypes.c_int32)]
+                                                                                      ("gibbs_generator", ctypes.c_int32)]
 
 
 _lib = None

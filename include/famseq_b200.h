@@ -191,7 +191,8 @@ typedef struct fs_info {
     int64_t mcmc_fixups;      /* chains the generated Gibbs kernel handed back (status 2) and the table-driven
                                * kernel redid; read from the device, so only exact once the work has completed */
     int32_t n_devices;        /* GPUs behind this engine (fs_create_multi), 1 for fs_create, 0 host-only        */
-    int32_t reserved;
+    int32_t gibbs_generator;  /* Gibbs kernel of the last MCMC launch: 0 table-driven, 1 generated dense sweeps,
+                               * 2 generated cached conditionals (csrc/cuda/gibbs_jit.cu)                        */
 } fs_info;
 int fs_get_info(const fs_engine *e, fs_info *out);
 

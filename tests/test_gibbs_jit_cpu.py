@@ -40,6 +40,7 @@ static inline size_t __cvta_generic_to_shared(const void *p) { return (size_t)((
 static inline double lds64(u32 a) { double v; std::memcpy(&v, smem_raw + a, 8); return v; }
 static inline double __ldcg(const double *p) { return *p; }
 static inline void atomicAdd(double *p, double v) { *p += v; }
+static inline void atomicAdd(u64 *p, u64 v) { *p += v; }
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __dsub_rn(double a, double b) { return a - b; }
@@ -102,7 +103,7 @@ def build_host_kernel(tmp_path, src: str):
     lib = ctypes.CDLL(so)
     P, I64, U64 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint64
     lib.famseq_gibbs.restype = None
-    lib.famseq_gibbs.argtypes = [P, P, P, P, P, P, I64, ctypes.c_int, ctypes.c_int, U64, I64, P, ctypes.c_int]
+    lib.famseq_gibbs.argtypes = [P, P, P, P, P, P, I64, ctypes.c_int, ctypes.c_int, U64, I64, P, ctypes.c_int, P]
     return lib
 
 
@@ -124,7 +125,7 @@ def test_generated_gibbs_code_reproduces_the_oracle(name, cols, V, tmp_path):
         post, single = np.zeros((S, 3)), np.zeros((S, 3))
         gt, status = np.zeros(S, np.uint8), np.full(1, 9, np.uint8)
         lib.famseq_gibbs(row_lk.ctypes.data, flag.ctypes.data, post.ctypes.data, single.ctypes.data, gt.ctypes.data, status.ctypes.data,
-                         1, burn, rep, seed, v_offset + v, scratch.ctypes.data, 1)
+                         1, burn, rep, seed, v_offset + v, scratch.ctypes.data, 1, None)
         if status[0] == 2:  # handed back to the table-driven kernel: legitimate only if a weight sum left the fast range
             assert not chain_stays_in_fast_range(ped, cols, lk[v:v + 1], fl[v:v + 1], burn, rep, seed, v_offset + v), f"{name} variant {v}"
             handed_back += 1
@@ -161,7 +162,7 @@ def test_status_2_is_raised_exactly_when_a_weight_sum_leaves_the_fast_range(tmp_
         post, single = np.zeros((S, 3)), np.zeros((S, 3))
         gt, status = np.zeros(S, np.uint8), np.full(1, 9, np.uint8)
         lib.famseq_gibbs(row_lk.ctypes.data, flag.ctypes.data, post.ctypes.data, single.ctypes.data, gt.ctypes.data, status.ctypes.data,
-                         1, burn, rep, seed, v_offset + v, scratch.ctypes.data, 1)
+                         1, burn, rep, seed, v_offset + v, scratch.ctypes.data, 1, None)
         gated = want["status"][v] == 1 and not np.any(want["single"][v])  # failed before the sampler started
         in_range = chain_stays_in_fast_range(ped, cols, lk[v:v + 1], fl[v:v + 1], burn, rep, seed, v_offset + v)
         if status[0] == 2:

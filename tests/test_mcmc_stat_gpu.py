@@ -100,3 +100,30 @@ def test_fixup_path_of_the_generated_kernel(pedname, monkeypatch):
     assert_same_chains(jit, table, f"fix-up/{pedname}")
     want = O.run(ped, cols, lk, fl, method=O.MCMC, burn=burn, rep=rep, rng=O.RNG_PHILOX, seed=99, v_offset=7)
     assert_parity(jit, want, 1e-9, f"fix-up/{pedname}")
+
+
+def test_pilot_picks_the_generator_that_suits_the_data(monkeypatch):
+    """Two generated Gibbs kernels (gibbs_jit.cu): cached conditionals, fast where the chains sit still, and dense sweeps,
+    whose speed does not depend on the data.  On the first large batch the engine runs a short pilot of the cached kernel and
+    counts how often its warps had to redo a group member by member: pedigree-consistent sequencing data keep the cached
+    kernel (fs_info.gibbs_generator == 2), Mendel-inconsistent likelihoods -- chains that keep moving -- switch the engine
+    to the dense one (1).  Either way the results are the oracle's."""
+    from famseq_b200 import synth
+    from oracle import oracle as O
+    from tests.util import assert_parity
+
+    monkeypatch.setenv("FAMSEQ_MCMC_JIT", "1")
+    monkeypatch.delenv("FAMSEQ_JIT_CACHED", raising=False)
+    ped = synth.ped14()
+    cols = ped.sequenced_cols()
+    V, burn, rep = 4096, 200, 1000
+    consistent, fl = synth.synth_likelihoods(ped, V, seed=31)
+    unrelated, _ = synth.synth_likelihoods(synth._mk([(i, 0, 0, 1) for i in range(1, len(cols) + 1)]), V, seed=32)
+    fl[:] = fl & 1
+    for lk, want_generator in ((consistent, 2), (unrelated, 1)):
+        with fs.Engine(ped.ids, ped.mids, ped.fids, ped.genders, cols, device=0) as e:
+            got = e.run(fs.MCMC, lk, fl, burn=burn, rep=rep, seed=4, v_offset=9)
+            assert e.info()["gibbs_generator"] == want_generator, e.info()
+        want = O.run(ped, cols, lk[:256], fl[:256], method=O.MCMC, burn=burn, rep=rep, rng=O.RNG_PHILOX, seed=4, v_offset=9)
+        head = fs.Result(got.post[:256], got.single[:256], got.gt[:256], got.status[:256])
+        assert_parity(head, want, 1e-9, f"pilot/{want_generator}")

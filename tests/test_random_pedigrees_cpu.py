@@ -88,7 +88,7 @@ def test_generated_gibbs_sampler_of_a_random_pedigree(seed, tmp_path):
         post, single = np.zeros((S, 3)), np.zeros((S, 3))
         gt, status = np.zeros(S, np.uint8), np.full(1, 9, np.uint8)
         lib.famseq_gibbs(row_lk.ctypes.data, flag.ctypes.data, post.ctypes.data, single.ctypes.data, gt.ctypes.data, status.ctypes.data,
-                         1, burn, rep, rng_seed, v_offset + v, scratch.ctypes.data, 1)
+                         1, burn, rep, rng_seed, v_offset + v, scratch.ctypes.data, 1, None)
         if status[0] == 2:  # legitimate only if a weight sum of this chain left the generated code's fast range
             assert not chain_stays_in_fast_range(ped, cols, lk[v:v + 1], fl[v:v + 1], burn, rep, rng_seed, v_offset + v), f"seed {seed} variant {v}"
             continue
