@@ -259,7 +259,7 @@ __device__ __forceinline__ bool peel(const NuclearParams &P, const VariantPriors
 // keeping the pedigree out).  FAST = true is the same arithmetic for the case that is nearly every variant -- default
 // -LRC 1, pedigree needed, nothing fails, every division in the divider's range -- without the tests for the others; it
 // returns true when the variant was not such a case, and the caller then runs the complete computation over it.
-template <int NC, bool PL, bool SINGLE, bool X, bool FAST>
+template <int NC, bool PL, bool SINGLE, bool X, bool FAST, bool IDENT>
 __device__ __forceinline__ bool variant_body(const NuclearParams &P, unsigned flag, const void *in_row, const double *__restrict__ lut,
                                              double *post_row, double *single_row, uint8_t *gt_row, uint8_t *status) {
     constexpr int NR = NC + 2;
@@ -275,13 +275,15 @@ __device__ __forceinline__ bool variant_body(const NuclearParams &P, unsigned fl
     }
     int col[NR];
     bool male[NR];
-    col[0] = P.col_father;
-    col[1] = P.col_mother;
+    // IDENT: every member sequenced, input columns in role order (father, mother, children) -- the column of a role is a
+    // literal and the address arithmetic of the row accesses folds away
+    col[0] = IDENT ? 0 : P.col_father;
+    col[1] = IDENT ? 1 : P.col_mother;
     male[0] = true;
     male[1] = false;
 #pragma unroll
     for (int c = 0; c < NC; c++) {
-        col[2 + c] = P.col_child[c];
+        col[2 + c] = IDENT ? 2 + c : P.col_child[c];
         male[2 + c] = P.male_child[c] != 0;
     }
     // individual-only posterior (family.cpp:1405-1499) and LRC gate (family.cpp:1140-1162)
@@ -348,7 +350,7 @@ __device__ __forceinline__ bool variant_body(const NuclearParams &P, unsigned fl
         }
     }
     if (failed) { // the reference returns false: every sample of the variant is reported as NA
-        const int S = C.s;
+        const int S = IDENT ? NR : C.s;
         for (int k = 0; k < 3 * S; k++) {
             post_row[k] = 0.0;
             if (SINGLE) single_row[k] = 0.0;
@@ -360,31 +362,31 @@ __device__ __forceinline__ bool variant_body(const NuclearParams &P, unsigned fl
 }
 
 // The complete computation, kept out of line: it runs for the few variants the fast pass hands over.
-template <int NC, bool PL, bool SINGLE>
+template <int NC, bool PL, bool SINGLE, bool IDENT>
 __device__ __noinline__ void variant_exact(const NuclearParams &P, unsigned flag, const void *in_row, const double *__restrict__ lut, double *post_row,
                                            double *single_row, uint8_t *gt_row, uint8_t *status) {
     if ((flag >> 1) & 1u)
-        variant_body<NC, PL, SINGLE, true, false>(P, flag, in_row, lut, post_row, single_row, gt_row, status);
+        variant_body<NC, PL, SINGLE, true, false, IDENT>(P, flag, in_row, lut, post_row, single_row, gt_row, status);
     else
-        variant_body<NC, PL, SINGLE, false, false>(P, flag, in_row, lut, post_row, single_row, gt_row, status);
+        variant_body<NC, PL, SINGLE, false, false, IDENT>(P, flag, in_row, lut, post_row, single_row, gt_row, status);
 }
 
-template <int NC, bool PL, bool SINGLE>
+template <int NC, bool PL, bool SINGLE, bool IDENT>
 __device__ __forceinline__ void variant_thread(const NuclearParams &P, unsigned flag, const void *in_row, const double *__restrict__ lut,
                                                double *post_row, double *single_row, uint8_t *gt_row, uint8_t *status) {
-    const bool redo = ((flag >> 1) & 1u) ? variant_body<NC, PL, SINGLE, true, true>(P, flag, in_row, lut, post_row, single_row, gt_row, status)
-                                         : variant_body<NC, PL, SINGLE, false, true>(P, flag, in_row, lut, post_row, single_row, gt_row, status);
-    if (redo) variant_exact<NC, PL, SINGLE>(P, flag, in_row, lut, post_row, single_row, gt_row, status);
+    const bool redo = ((flag >> 1) & 1u) ? variant_body<NC, PL, SINGLE, true, true, IDENT>(P, flag, in_row, lut, post_row, single_row, gt_row, status)
+                                         : variant_body<NC, PL, SINGLE, false, true, IDENT>(P, flag, in_row, lut, post_row, single_row, gt_row, status);
+    if (redo) variant_exact<NC, PL, SINGLE, IDENT>(P, flag, in_row, lut, post_row, single_row, gt_row, status);
 }
 
 // PL = compact input (uint16 Phred-scaled likelihoods + decode table), SINGLE = the caller wants the individual-only
 // posteriors too (B.single != nullptr).
-template <int NC, int TB, bool PL, bool SINGLE>
+template <int NC, int TB, bool PL, bool SINGLE, bool IDENT>
 __global__ void __launch_bounds__(TB, NC == 1 ? 896 / TB : 1) es_nuclear_kernel(const __grid_constant__ NuclearParams P, const BatchPtrs B) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     using In = typename std::conditional<PL, uint16_t, double>::type;
     const RunConstants &C = P.C;
-    const int S = C.s, S3 = 3 * S;
+    const int S = IDENT ? NC + 2 : C.s, S3 = 3 * S;
     const unsigned out_bytes = (unsigned)(TB * S3 * sizeof(double));
     const unsigned in_bytes = (unsigned)(TB * S3 * sizeof(In)); // 192 S (PL) or 768 S bytes per 32 variants: a multiple of 16
     double *s_post = reinterpret_cast<double *>(smem_raw); // [TB][S][3]
@@ -424,7 +426,7 @@ __global__ void __launch_bounds__(TB, NC == 1 ? 896 / TB : 1) es_nuclear_kernel(
         block_sync();
 
     if (tid < nv)
-        variant_thread<NC, PL, SINGLE>(P, flag, s_in + tid * S3, B.lut, s_post + tid * S3, s_single + tid * S3, s_gt + tid * S, s_status + tid);
+        variant_thread<NC, PL, SINGLE, IDENT>(P, flag, s_in + tid * S3, B.lut, s_post + tid * S3, s_single + tid * S3, s_gt + tid * S, s_status + tid);
 
     if (full) {
         fence_async_smem(); // make this thread's shared-memory writes visible to the TMA engine
@@ -447,15 +449,23 @@ __global__ void __launch_bounds__(TB, NC == 1 ? 896 / TB : 1) es_nuclear_kernel(
     }
 }
 
-template <int NC, int TB, bool PL, bool SINGLE> cudaError_t launch_io(const NuclearParams &P, const BatchPtrs &B, cudaStream_t stream) {
+template <int NC, int TB, bool PL, bool SINGLE, bool IDENT> cudaError_t launch_ident(const NuclearParams &P, const BatchPtrs &B, cudaStream_t stream) {
     const size_t S = (size_t)P.C.s;
     const size_t in_bytes = (TB * S * 3 * (PL ? sizeof(uint16_t) : sizeof(double)) + 15) & ~(size_t)15;
     const size_t smem = (SINGLE ? 2 : 1) * TB * S * 3 * sizeof(double) + in_bytes + ((TB * S + 15) & ~(size_t)15) + TB;
-    cudaError_t rc = cudaFuncSetAttribute(es_nuclear_kernel<NC, TB, PL, SINGLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t rc = cudaFuncSetAttribute(es_nuclear_kernel<NC, TB, PL, SINGLE, IDENT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (rc != cudaSuccess) return rc;
     const unsigned grid = (unsigned)((B.V + TB - 1) / TB);
-    es_nuclear_kernel<NC, TB, PL, SINGLE><<<grid, TB, smem, stream>>>(P, B);
+    es_nuclear_kernel<NC, TB, PL, SINGLE, IDENT><<<grid, TB, smem, stream>>>(P, B);
     return cudaGetLastError();
+}
+
+template <int NC, int TB, bool PL, bool SINGLE> cudaError_t launch_io(const NuclearParams &P, const BatchPtrs &B, cudaStream_t stream) {
+    bool ident = P.allow_ident && P.C.s == NC + 2 && P.col_father == 0 && P.col_mother == 1;
+    for (int c = 0; c < NC; c++) ident = ident && P.col_child[c] == 2 + c;
+    // the specialisation for the identity column map exists for the headline tile size only (compile time)
+    if (ident && TB == 32) return launch_ident<NC, 32, PL, SINGLE, true>(P, B, stream);
+    return launch_ident<NC, TB, PL, SINGLE, false>(P, B, stream);
 }
 
 template <int NC, int TB> cudaError_t launch_nc(const NuclearParams &P, const BatchPtrs &B, cudaStream_t stream) {
