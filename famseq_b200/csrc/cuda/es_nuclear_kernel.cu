@@ -463,8 +463,12 @@ template <int NC, int TB, bool PL, bool SINGLE, bool IDENT> cudaError_t launch_i
 template <int NC, int TB, bool PL, bool SINGLE> cudaError_t launch_io(const NuclearParams &P, const BatchPtrs &B, cudaStream_t stream) {
     bool ident = P.allow_ident && P.C.s == NC + 2 && P.col_father == 0 && P.col_mother == 1;
     for (int c = 0; c < NC; c++) ident = ident && P.col_child[c] == 2 + c;
-    // the specialisation for the identity column map exists for the headline tile size only (compile time)
-    if (ident && TB == 32) return launch_ident<NC, 32, PL, SINGLE, true>(P, B, stream);
+    // The specialisation for the identity column map (headline tile size only: compile time) saves ~120 of ~800 instructions per
+    // trio variant, at the price of a few spilled registers under the 72-register cap.  Measured (profiles/r2j): compact input
+    // 0.334 -> 0.317 ms (post + single), 0.282 -> 0.257 ms (post only) per 10 M trio variants; quads 0.53 -> 0.60, three-child
+    // sibships 0.61 -> 0.69 of the HBM roofline; but the FP64-input trio kernel, which is HBM-bound, loses (0.345 -> 0.350 ms),
+    // so that one keeps the general code.
+    if (ident && TB == 32 && (PL || NC > 1)) return launch_ident<NC, 32, PL, SINGLE, true>(P, B, stream);
     return launch_ident<NC, TB, PL, SINGLE, false>(P, B, stream);
 }
 
