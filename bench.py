@@ -19,7 +19,7 @@ sites, no data-path collective).  A "step" is one pass of the kernel over the ra
              reference sources) on all host cores, one pass over the whole 10 M-variant configuration
   cli_e2e  : file -> file through this repo's FamSeq command line; ref_cuda_bn: the reference's own CUDA build
 `--impl reference` times that CPU engine as the reference arm (same metric string, same sample definition).
-`--single-process` (N > 1) adds the e2e of ONE fs_create_multi engine over all N GPUs writing one ordered buffer.
+For N > 1 the line also carries `e2e_single_process`: ONE fs_create_multi engine over all N GPUs writing one ordered buffer.
 """
 from __future__ import annotations
 
@@ -471,8 +471,9 @@ def main():
     ap.add_argument("--cli-variants", type=int, default=2_000_000)
     ap.add_argument("--methods", default="es,es14,bn,mcmc,cli,refgpu", help="which lines to time (es is the headline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--single-process", action="store_true",
-                    help="e2e of N GPUs through ONE fs_create_multi engine writing one ordered host buffer (rank 0 drives all GPUs)")
+    ap.add_argument("--single-process", action="store_true", help="(default for N > 1; kept for compatibility)")
+    ap.add_argument("--no-single-process", action="store_true",
+                    help="N > 1: skip the e2e of ONE fs_create_multi engine over all N GPUs writing one ordered host buffer (rank 0 drives all GPUs)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -597,9 +598,8 @@ def main():
     })
 
     # ---- N GPUs behind ONE engine, one ordered host buffer (rank 0 drives every GPU) ---------------------------
-    if args.single_process and world > 1:
-        if world > 1:
-            dist.barrier()
+    if world > 1 and not args.no_single_process:
+        dist.barrier()
         if rank == 0:
             VV = world * args.variants
             pl, fl = synth.synth_pl(trio, args.variants, SEED + 2)

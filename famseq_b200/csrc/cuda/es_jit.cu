@@ -30,7 +30,18 @@ namespace famseq {
 
 namespace {
 
-constexpr int kTB = 32;
+// Variants (threads) per block.  One warp per block moves its tile with the least synchronisation; several warps per block start
+// together and walk the (long, straight-line) program roughly in step, which keeps their instruction fetches in the same
+// cache lines.  FAMSEQ_ES_JIT_TB (32 .. 256, multiple of 32) picks it; see es_jit_tb().
+int es_jit_tb() {
+    static const int tb = [] {
+        const char *env = std::getenv("FAMSEQ_ES_JIT_TB");
+        const int v = env ? std::atoi(env) : 32;
+        return (v >= 32 && v <= 256 && v % 32 == 0) ? v : 32;
+    }();
+    return tb;
+}
+#define kTB es_jit_tb()
 
 std::string lit(double x) {
     unsigned long long u;
