@@ -321,8 +321,6 @@ int fs_create(const fs_pedigree *ped, const fs_params *params, int device, fs_en
                     np.n_children++;
                 }
             e->is_nuclear = true;
-            np.tb = 32;
-            if (const char *env = std::getenv("FAMSEQ_ES_TB")) np.tb = std::atoi(env) == 64 ? 64 : 32;
             np.allow_ident = 1;
             if (const char *env = std::getenv("FAMSEQ_ES_IDENT")) np.allow_ident = env[0] != '0';
         }

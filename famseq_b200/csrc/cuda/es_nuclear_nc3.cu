@@ -1,0 +1,6 @@
+// es_nuclear_nc3.cu -- the nuclear-family Elston-Stewart kernel (es_nuclear_kernel.cuh) for sibships of 3.
+#include "es_nuclear_kernel.cuh"
+
+namespace famseq {
+cudaError_t launch_es_nuclear_nc3(const NuclearParams &P, const BatchPtrs &B, cudaStream_t stream) { return launch_nc<3, 32>(P, B, stream); }
+} // namespace famseq

@@ -31,7 +31,6 @@ struct NuclearParams {
     int32_t col_father, col_mother;               // input column or -1
     int32_t col_child[ES_NUCLEAR_MAX_CHILDREN];   // children in ped order
     int32_t male_child[ES_NUCLEAR_MAX_CHILDREN];
-    int32_t tb; // variants per block (32 or 64; FAMSEQ_ES_TB, read once in fs_create)
     int32_t allow_ident; // use the kernel specialised for the identity column map when it applies (FAMSEQ_ES_IDENT=0 turns it off)
 };
 // Handles B.pl (compact input, decoded through B.lut) and B.single == nullptr itself.
