@@ -9,9 +9,12 @@
 //   * every message is a set of named doubles (SSA), so operands live in registers and the compiler schedules the
 //     whole pedigree as two basic blocks (autosomal and chrX rules);
 //   * transmission-table entries are literal constants (constant-bank operands of the FP64 instructions);
-//   * one warp per block and one variant per thread: the block's likelihood tile arrives through one TMA bulk copy,
-//     each thread pulls its row into registers, writes its `single` row into a second tile and its `post` row over
-//     its own input row, and both tiles leave through TMA bulk stores (as in es_nuclear_kernel.cu).
+//   * one warp per block, one variant per thread, and every block walks a strided list of 32-variant tiles with the copies of
+//     neighbouring tiles running under the arithmetic (see the kernel text below): tile k+1 arrives through a TMA bulk copy
+//     while tile k is peeled, the `single` rows leave as soon as they exist and the posterior rows when the tile is done, and
+//     nothing waits for a store except the one that needs its buffer back, thousands of cycles later.  (Round 1 / early round
+//     2: one tile per block -- the warp sat idle for 18 % of its life waiting for its tile to arrive and for its stores to
+//     drain, profiles/r2i_r2i_es14.txt, and with 255 registers there are only two warps per scheduler to cover for it.)
 // Same operations in the same order as the interpreter (no FMA contraction, the same shared-reciprocal division), so
 // the results are the same doubles; the only liberty is that sums start from their first term instead of from 0.0,
 // which can only change the sign of a zero.  tests/test_parity_gpu.py compares both kernels bit for bit.
@@ -30,18 +33,7 @@ namespace famseq {
 
 namespace {
 
-// Variants (threads) per block.  One warp per block moves its tile with the least synchronisation; several warps per block start
-// together and walk the (long, straight-line) program roughly in step, which keeps their instruction fetches in the same
-// cache lines.  FAMSEQ_ES_JIT_TB (32 .. 256, multiple of 32) picks it; see es_jit_tb().
-int es_jit_tb() {
-    static const int tb = [] {
-        const char *env = std::getenv("FAMSEQ_ES_JIT_TB");
-        const int v = env ? std::atoi(env) : 32;
-        return (v >= 32 && v <= 256 && v % 32 == 0) ? v : 32;
-    }();
-    return tb;
-}
-#define kTB es_jit_tb()
+constexpr int kTB = 32; // variants per tile = threads per block: one warp (several warps per block were tried, profiles/r2l_es14.log)
 
 std::string lit(double x) {
     unsigned long long u;
@@ -87,10 +79,9 @@ __device__ __forceinline__ void bulk_store(void *gmem_dst, const void *smem_src,
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes)
                  : "memory");
 }
-__device__ __forceinline__ void bulk_commit_and_wait_read() {
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // x[0..2] / s, correctly rounded: shared reciprocal + one Markstein correction, exponent-guarded (cuda/common.cuh: div3)
@@ -125,6 +116,32 @@ __device__ __forceinline__ u8 call_genotype(double p0, double p1, double p2) {
     if (big < p1) { big = p1; arg = 1; }
     if (big < p2) { big = p2; arg = 2; }
     return (u8)arg;
+}
+
+// The point of a tile's program where its buffers change hands (once per tile, all 32 lanes together; the generator puts it
+// in front of the first posterior row the program writes, a quarter of the way in).  By now the stores issued before it --
+// the previous tile's posterior rows out of B, this tile's `single` rows out of A -- have long been read by the copy engine,
+// so the wait costs nothing; B then starts as a copy of A (a member's posterior is its individual-only posterior until the
+// pedigree says otherwise, family.cpp:1164-1253) and A is free for the next tile's likelihoods.
+struct Pipe {
+    double *a, *b;          // A: likelihood rows in, then `single` rows out; B: posterior rows out
+    u64 *bar;
+    const double *next_lk;  // the next full tile of this block, or nullptr
+    int lane;
+    bool done;
+};
+__device__ __forceinline__ void pipeline_point(Pipe &p) {
+    if (p.done) return;
+    p.done = true;
+    if (p.lane == 0) bulk_wait_read();
+    __syncwarp();
+    for (int k = p.lane; k < TB * S3; k += TB) p.b[k] = p.a[k];
+    fence_async_smem(); // order this lane's reads of A before the copy engine's writes to it
+    __syncwarp();
+    if (p.lane == 0 && p.next_lk) {
+        mbar_expect_tx(p.bar, (unsigned)(TB * S3 * sizeof(double)));
+        bulk_load(p.a, p.next_lk, (unsigned)(TB * S3 * sizeof(double)), p.bar);
+    }
 }
 )CUDA";
 
@@ -227,9 +244,11 @@ class Emitter {
                 o_ << "    if (" << t << "sum == 0.0) failed = true;\n";
                 if ((w0 >> 8) & 1u) {
                     const int col = (int)(w0 >> 9);
+                    if (!point_emitted_) o_ << "    pipeline_point(pipe);\n";
+                    point_emitted_ = true;
                     o_ << "    { double q0, q1, q2; div3(" << t << "m0, " << t << "m1, " << t << "m2, " << t << "sum, q0, q1, q2);\n"
-                       << "      row[" << col * 3 << "] = q0; row[" << col * 3 + 1 << "] = q1; row[" << col * 3 + 2 << "] = q2; gt_row[" << col
-                       << "] = call_genotype(q0, q1, q2); }\n";
+                       << "      if (mine) { row[" << col * 3 << "] = q0; row[" << col * 3 + 1 << "] = q1; row[" << col * 3 + 2 << "] = q2; gt_row[" << col
+                       << "] = call_genotype(q0, q1, q2); } }\n";
                 }
                 pc += 3;
             }
@@ -244,6 +263,7 @@ class Emitter {
     int S_;
     std::vector<int> cur_; // SSA version of every scratch slot
     int n_def_ = 0, n_tmp_ = 0;
+    bool point_emitted_ = false;
 
     std::string tmp() { return (x_ ? "xt" : "at") + std::to_string(n_tmp_++) + "_"; }
     // name prefix of operand u; components are prefix + "0/1/2"
@@ -278,8 +298,10 @@ std::string es_jit_source(const EsParams &P) {
     o << "0};\n";
     const unsigned unseq = (C.unseq_fail[0] ? 1u : 0u) | (C.unseq_fail[1] ? 2u : 0u) | (C.unseq_fail[2] ? 4u : 0u) | (C.unseq_fail[3] ? 8u : 0u);
     for (int x = 0; x < 2; x++) {
-        o << "\n// the message program with the " << (x ? "chrX" : "autosomal") << " rules; returns true when a member's row sum was exactly zero\n"
-          << "__device__ __forceinline__ bool peel_" << (x ? "x" : "a") << "(double *row, u8 *gt_row, double pa0, double pa1, double pa2, double pm0, double pm1, double pm2";
+        o << "\n// the message program with the " << (x ? "chrX" : "autosomal") << " rules, run by all 32 lanes together; lanes with `mine` keep their rows.\n"
+          << "// Returns true when a member's row sum was exactly zero\n"
+          << "__device__ __forceinline__ bool peel_" << (x ? "x" : "a")
+          << "(Pipe &pipe, bool mine, double *row, u8 *gt_row, double pa0, double pa1, double pa2, double pm0, double pm1, double pm2";
         for (int c = 0; c < S; c++)
             for (int g = 0; g < 3; g++) o << ", double L" << c << "_" << g;
         o << ") {\n    bool failed = false;\n";
@@ -288,95 +310,129 @@ std::string es_jit_source(const EsParams &P) {
     }
     int min_blocks = 0; // tuning knob: resident blocks per SM the register allocation is forced to allow
     if (const char *env = std::getenv("FAMSEQ_ES_JIT_BLOCKS")) min_blocks = std::max(0, std::min(32, std::atoi(env)));
-    o << "\nextern \"C\" __global__ void __launch_bounds__(TB" << (min_blocks ? ", " + std::to_string(min_blocks) : std::string()) << ")\n"
+    o << "\n#define GT_BYTES ((TB * NCOL + 15) & ~15)\n"
+      << "extern \"C\" __global__ void __launch_bounds__(TB" << (min_blocks ? ", " + std::to_string(min_blocks) : std::string()) << ")\n"
       << "famseq_es(const double *__restrict__ lk, const u8 *__restrict__ flags, double *__restrict__ post, double *__restrict__ single,\n"
       << "          u8 *__restrict__ gt, u8 *__restrict__ status, i64 V) {\n"
       << "    extern __shared__ __align__(128) unsigned char smem_raw[];\n"
-      << "    double *s_tile = (double *)smem_raw;   // [TB][S3] likelihood rows in, posterior rows out\n"
-      << "    double *s_single = s_tile + TB * S3;   // [TB][S3]\n"
-      << "    u8 *s_gt = (u8 *)(s_single + TB * S3); // [TB][NCOL]\n"
-      << "    u8 *s_status = s_gt + ((TB * NCOL + 15) & ~15);\n"
+      << "    double *s_a = (double *)smem_raw;   // [TB][S3] A: likelihood rows in, `single` rows out\n"
+      << "    double *s_b = s_a + TB * S3;        // [TB][S3] B: posterior rows out\n"
+      << "    u8 *s_gt2 = (u8 *)(s_b + TB * S3);  // [2][TB][NCOL]  (these two alternate between tiles: their stores are only\n"
+      << "    u8 *s_status2 = s_gt2 + 2 * GT_BYTES; // [2][TB]       waited for one tile later)\n"
       << "    __shared__ u64 bar;\n"
-      << "    const int tid = threadIdx.x;\n"
-      << "    const i64 v0 = (i64)blockIdx.x * TB;\n"
-      << "    const int nv = (int)((V - v0) < (i64)TB ? (V - v0) : (i64)TB);\n"
-      << "    const bool full = nv == TB; // full tiles go through TMA; the ragged last tile uses plain loads / stores\n"
+      << "    const int lane = threadIdx.x;\n"
       << "    const unsigned tile_bytes = (unsigned)(TB * S3 * sizeof(double));\n"
-      << "    if (full) {\n"
-      << "        if (tid == 0) mbar_init(&bar, 1);\n"
-      << "        __syncthreads();\n"
-      << "        if (tid == 0) { mbar_expect_tx(&bar, tile_bytes); bulk_load(s_tile, lk + v0 * S3, tile_bytes, &bar); }\n"
-      << "    } else {\n"
-      << "        for (int k = tid; k < nv * S3; k += TB) s_tile[k] = lk[v0 * S3 + k];\n"
+      << "    const i64 n_tiles = (V + TB - 1) / TB, n_full = V / TB; // tiles below n_full move by TMA; a ragged last tile by plain loads / stores\n"
+      << "    i64 tile = blockIdx.x;\n"
+      << "    if (tile >= n_tiles) return;\n"
+      << "    if (lane == 0) {\n"
+      << "        mbar_init(&bar, 1);\n"
+      << "        if (tile < n_full) { mbar_expect_tx(&bar, tile_bytes); bulk_load(s_a, lk + tile * TB * S3, tile_bytes, &bar); }\n"
       << "    }\n"
-      << "    u32 flag = 0;\n"
-      << "    if (tid < nv && flags) flag = flags[v0 + tid];\n"
+      << "    __syncwarp();\n"
+      << "    u32 flag_next = (flags && tile * TB + lane < V) ? flags[tile * TB + lane] : 0u;\n"
+      << "    unsigned phase = 0, it = 0;\n"
+      << "    for (; tile < n_tiles; tile += gridDim.x, it ^= 1u) {\n"
+      << "    const i64 v0 = tile * TB, next = tile + gridDim.x;\n"
+      << "    const int nv = (int)((V - v0) < (i64)TB ? (V - v0) : (i64)TB);\n"
+      << "    const bool full = nv == TB;\n"
+      << "    const u32 flag = flag_next;\n"
+      << "    flag_next = (flags && next * TB + lane < V) ? flags[next * TB + lane] : 0u; // arrives while this tile is peeled\n"
       << "    const bool known = flag & 1u, chrx = (flag >> 1) & 1u;\n";
     for (int g = 0; g < 3; g++)
         o << "    const double pa" << g << " = known ? " << lit(C.prior[1][g]) << " : " << lit(C.prior[0][g]) << ";\n"
           << "    const double pm" << g << " = chrx ? (known ? " << lit(C.prior[3][g]) << " : " << lit(C.prior[2][g]) << ") : pa" << g << ";\n";
-    o << "    if (full) mbar_wait(&bar, 0); else __syncthreads();\n"
-      << "    if (tid < nv) {\n"
-      << "        double *row = s_tile + tid * S3, *single_row = s_single + tid * S3;\n"
-      << "        u8 *gt_row = s_gt + tid * NCOL;\n";
+    o << "    if (full) {\n"
+      << "        mbar_wait(&bar, phase);\n"
+      << "        phase ^= 1u;\n"
+      << "    } else {\n"
+      << "        // (A is free: the previous tile's pipeline point saw its `single` store off and fetched nothing)\n"
+      << "        for (int k = lane; k < TB * S3; k += TB) s_a[k] = k < nv * S3 ? lk[v0 * S3 + k] : 0.0;\n"
+      << "        __syncwarp();\n"
+      << "    }\n"
+      << "    Pipe pipe;\n"
+      << "    pipe.a = s_a; pipe.b = s_b; pipe.bar = &bar; pipe.lane = lane; pipe.done = false;\n"
+      << "    pipe.next_lk = next < n_full ? lk + next * TB * S3 : nullptr;\n"
+      << "    double *row = s_b + lane * S3, *single_row = s_a + lane * S3;\n"
+      << "    u8 *s_gt = s_gt2 + it * GT_BYTES, *s_status = s_status2 + it * TB;\n"
+      << "    u8 *gt_row = s_gt + lane * NCOL;\n"
+      << "    const bool live = lane < nv;\n";
     for (int c = 0; c < S; c++)
-        o << "        const double L" << c << "_0 = row[" << c * 3 << "], L" << c << "_1 = row[" << c * 3 + 1 << "], L" << c << "_2 = row[" << c * 3 + 2 << "];\n";
-    o << "        // individual-only posterior (family.cpp:1405-1499) and LRC gate (family.cpp:1140-1162); the posterior row starts\n"
-      << "        // as a copy of it and stays that way when the gate keeps the pedigree out (family.cpp:1164-1253)\n"
-      << "        bool failed = (" << unseq << "u >> (flag & 3u)) & 1u;\n"
-      << "        bool pedigree_needed = false;\n"
-      << "        const double lrc = " << lit(C.lrc) << ";\n";
+        o << "    const double L" << c << "_0 = single_row[" << c * 3 << "], L" << c << "_1 = single_row[" << c * 3 + 1 << "], L" << c << "_2 = single_row[" << c * 3 + 2
+          << "];\n";
+    o << "    // individual-only posterior (family.cpp:1405-1499) and LRC gate (family.cpp:1140-1162)\n"
+      << "    bool failed = (" << unseq << "u >> (flag & 3u)) & 1u;\n"
+      << "    bool pedigree_needed = false;\n"
+      << "    const double lrc = " << lit(C.lrc) << ";\n";
     for (int c = 0; c < S; c++) {
         const char *pr = C.col_male[c] ? "pm" : "pa";
-        o << "        {\n"
-          << "            const double r0 = __dmul_rn(L" << c << "_0, " << pr << "0), r1 = __dmul_rn(L" << c << "_1, " << pr << "1), r2 = __dmul_rn(L" << c << "_2, " << pr << "2);\n"
-          << "            const double rs = __dadd_rn(__dadd_rn(r0, r1), r2);\n"
-          << "            if (rs <= 0.0) failed = true;\n"
-          << "            double q0, q1, q2; div3(r0, r1, r2, rs, q0, q1, q2);\n"
-          << "            single_row[" << c * 3 << "] = q0; single_row[" << c * 3 + 1 << "] = q1; single_row[" << c * 3 + 2 << "] = q2;\n"
-          << "            row[" << c * 3 << "] = q0; row[" << c * 3 + 1 << "] = q1; row[" << c * 3 + 2 << "] = q2;\n"
-          << "            gt_row[" << c << "] = call_genotype(q0, q1, q2);\n"
-          << "            double big = 0.0;\n"
-          << "            if (big < L" << c << "_0) big = L" << c << "_0;\n"
-          << "            if (big < L" << c << "_1) big = L" << c << "_1;\n"
-          << "            if (big < L" << c << "_2) big = L" << c << "_2;\n"
-          << "            if (lrc_wants_pedigree(lrc, L" << c << "_0, L" << c << "_1, L" << c << "_2, big, __dadd_rn(__dadd_rn(L" << c << "_0, L" << c << "_1), L" << c
+        o << "    {\n"
+          << "        const double r0 = __dmul_rn(L" << c << "_0, " << pr << "0), r1 = __dmul_rn(L" << c << "_1, " << pr << "1), r2 = __dmul_rn(L" << c << "_2, " << pr << "2);\n"
+          << "        const double rs = __dadd_rn(__dadd_rn(r0, r1), r2);\n"
+          << "        if (rs <= 0.0) failed = true;\n"
+          << "        double q0, q1, q2; div3(r0, r1, r2, rs, q0, q1, q2);\n"
+          << "        single_row[" << c * 3 << "] = q0; single_row[" << c * 3 + 1 << "] = q1; single_row[" << c * 3 + 2 << "] = q2;\n"
+          << "        gt_row[" << c << "] = call_genotype(q0, q1, q2);\n"
+          << "        double big = 0.0;\n"
+          << "        if (big < L" << c << "_0) big = L" << c << "_0;\n"
+          << "        if (big < L" << c << "_1) big = L" << c << "_1;\n"
+          << "        if (big < L" << c << "_2) big = L" << c << "_2;\n"
+          << "        if (lrc_wants_pedigree(lrc, L" << c << "_0, L" << c << "_1, L" << c << "_2, big, __dadd_rn(__dadd_rn(L" << c << "_0, L" << c << "_1), L" << c
           << "_2))) pedigree_needed = true;\n"
-          << "        }\n";
+          << "    }\n";
     }
-    auto call = [&](const char *fn) {
-        o << fn << "(row, gt_row, pa0, pa1, pa2, pm0, pm1, pm2";
+    auto call = [&](const char *fn, const char *mine) {
+        o << fn << "(pipe, " << mine << ", row, gt_row, pa0, pa1, pa2, pm0, pm1, pm2";
         for (int c = 0; c < S; c++)
             for (int g = 0; g < 3; g++) o << ", L" << c << "_" << g;
         o << ")";
     };
-    o << "        if (!failed && pedigree_needed) {\n            if (chrx) failed = ";
-    call("peel_x");
-    o << ";\n            else failed = ";
-    call("peel_a");
-    o << ";\n        }\n"
-      << "        if (failed) {\n"
-      << "            for (int k = 0; k < S3; k++) row[k] = single_row[k] = 0.0;\n"
-      << "            for (int c = 0; c < NCOL; c++) gt_row[c] = 255;\n"
-      << "        }\n"
-      << "        s_status[tid] = failed ? 1 : 0;\n"
+    o << "    const bool failed_early = failed;\n"
+      << "    if (failed) for (int k = 0; k < S3; k++) single_row[k] = 0.0;\n"
+      << "    fence_async_smem(); // this lane's shared-memory writes, for the copy engine\n"
+      << "    __syncwarp();\n"
+      << "    if (full && lane == 0) { bulk_store(single + v0 * S3, s_a, tile_bytes); bulk_commit(); }\n"
+      << "    // the pedigree: the warp runs a rule set when any of its variants wants it, and only those variants keep the rows\n"
+      << "    const bool want = live && !failed && pedigree_needed;\n"
+      << "    const bool mine_a = want && !chrx, mine_x = want && chrx;\n"
+      << "    if (__any_sync(0xffffffffu, mine_a)) { const bool f = ";
+    call("peel_a", "mine_a");
+    o << "; if (mine_a && f) failed = true; }\n"
+      << "    if (__any_sync(0xffffffffu, mine_x)) { const bool f = ";
+    call("peel_x", "mine_x");
+    o << "; if (mine_x && f) failed = true; }\n"
+      << "    pipeline_point(pipe); // (a tile the gate kept the pedigree out of altogether)\n"
+      << "    if (failed) {\n"
+      << "        for (int k = 0; k < S3; k++) row[k] = 0.0;\n"
+      << "        for (int c = 0; c < NCOL; c++) gt_row[c] = 255;\n"
       << "    }\n"
+      << "    s_status[lane] = failed ? 1 : 0;\n"
       << "    if (full) {\n"
-      << "        fence_async_smem(); // make this thread's shared-memory writes visible to the TMA engine\n"
-      << "        __syncthreads();\n"
-      << "        if (tid == 0) {\n"
-      << "            bulk_store(post + v0 * S3, s_tile, tile_bytes);\n"
-      << "            bulk_store(single + v0 * S3, s_single, tile_bytes);\n"
+      << "        fence_async_smem();\n"
+      << "        __syncwarp();\n"
+      << "        if (lane == 0) {\n"
+      << "            bulk_store(post + v0 * S3, s_b, tile_bytes);\n"
       << "            bulk_store(gt + v0 * NCOL, s_gt, (unsigned)(TB * NCOL));\n"
       << "            bulk_store(status + v0, s_status, (unsigned)TB);\n"
-      << "            bulk_commit_and_wait_read(); // shared memory must stay alive until the engine has read it\n"
+      << "            bulk_commit();\n"
+      << "        }\n"
+      << "        // a row sum that vanished inside the pedigree (family.cpp:1376-1384) clears `single` too, and that row is on its way\n"
+      << "        // out already: let the copy land, then overwrite it\n"
+      << "        if (__any_sync(0xffffffffu, failed && !failed_early)) {\n"
+      << "            if (lane == 0) bulk_wait_all();\n"
+      << "            __syncwarp();\n"
+      << "            if (failed && !failed_early) for (int k = 0; k < S3; k++) single[(v0 + lane) * S3 + k] = 0.0;\n"
       << "        }\n"
       << "    } else {\n"
-      << "        __syncthreads();\n"
-      << "        for (int k = tid; k < nv * S3; k += TB) { post[v0 * S3 + k] = s_tile[k]; single[v0 * S3 + k] = s_single[k]; }\n"
-      << "        for (int k = tid; k < nv * NCOL; k += TB) gt[v0 * NCOL + k] = s_gt[k];\n"
-      << "        if (tid < nv) status[v0 + tid] = s_status[tid];\n"
+      << "        __syncwarp();\n"
+      << "        if (failed && !failed_early) for (int k = 0; k < S3; k++) single_row[k] = 0.0;\n"
+      << "        __syncwarp();\n"
+      << "        for (int k = lane; k < nv * S3; k += TB) { post[v0 * S3 + k] = s_b[k]; single[v0 * S3 + k] = s_a[k]; }\n"
+      << "        for (int k = lane; k < nv * NCOL; k += TB) gt[v0 * NCOL + k] = s_gt[k];\n"
+      << "        if (live) status[v0 + lane] = s_status[lane];\n"
       << "    }\n"
+      << "    }\n"
+      << "    if (lane == 0) bulk_wait_read(); // shared memory must stay alive until the copy engine has read it\n"
       << "}\n";
     return o.str();
 }
@@ -393,11 +449,12 @@ struct EsJitKernel {
     cudaLibrary_t library = nullptr;
     cudaKernel_t kernel = nullptr;
     size_t smem = 0;
+    int64_t max_blocks = 0; // resident blocks of the whole device: the grid of the tile loop
 };
 
 static size_t es_jit_smem(const EsParams &P) {
     const size_t S = (size_t)P.C.s;
-    return 2 * kTB * S * 3 * sizeof(double) + ((kTB * S + 15) & ~(size_t)15) + kTB;
+    return 2 * kTB * S * 3 * sizeof(double) + 2 * (((kTB * S + 15) & ~(size_t)15) + kTB);
 }
 
 // Register-resident straight-line code only pays for pedigrees of moderate size: beyond ~24 sequenced members the
@@ -422,6 +479,18 @@ int es_jit_load(const EsParams &P, const std::string &cubin, EsJitKernel **out, 
     if (e != cudaSuccess) return cuda_err(e, "cudaLibraryGetKernel");
     e = cudaFuncSetAttribute((const void *)k->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k->smem);
     if (e != cudaSuccess) return cuda_err(e, "cudaFuncSetAttribute(shared memory)");
+    int device = 0, n_sm = 0, per_sm = 0;
+    e = cudaGetDevice(&device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void *)k->kernel, kTB, k->smem);
+    if (e != cudaSuccess) return cuda_err(e, "occupancy query");
+    if (per_sm < 1) {
+        err = "ES JIT: the generated kernel does not fit on a multiprocessor";
+        es_jit_unload(k);
+        return FS_E_CUDA;
+    }
+    if (const char *env = std::getenv("FAMSEQ_ES_JIT_GRID")) per_sm = std::max(1, std::min(per_sm * 4, std::atoi(env))); // tuning: blocks per SM in the grid
+    k->max_blocks = (int64_t)n_sm * per_sm;
     *out = k;
     return FS_OK;
 }
@@ -435,14 +504,14 @@ void es_jit_unload(EsJitKernel *k) {
 cudaError_t es_jit_launch(EsJitKernel *k, const BatchPtrs &B, cudaStream_t stream) {
     if (B.V <= 0) return cudaSuccess;
     const int64_t n_tiles = (B.V + kTB - 1) / kTB;
-    if (n_tiles > 0x7fffffff) return cudaErrorInvalidValue;
+    const int64_t grid = std::min(n_tiles, k->max_blocks);
     const double *lk = B.lk;
     const uint8_t *flags = B.flags;
     double *post = B.post, *single = B.single;
     uint8_t *gt = B.gt, *status = B.status;
     long long V = B.V;
     void *args[] = {&lk, &flags, &post, &single, &gt, &status, &V};
-    return cudaLaunchKernel((const void *)k->kernel, dim3((unsigned)n_tiles), dim3(kTB), args, k->smem, stream);
+    return cudaLaunchKernel((const void *)k->kernel, dim3((unsigned)grid), dim3(kTB), args, k->smem, stream);
 }
 
 } // namespace famseq

@@ -26,6 +26,8 @@ static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __longlong_as_double(long long x) { double d; std::memcpy(&d, &x, 8); return d; }
 static inline void div3(double x0, double x1, double x2, double s, double &q0, double &q1, double &q2) { q0 = x0 / s; q1 = x1 / s; q2 = x2 / s; }
+struct Pipe {};                                   // the tile pipeline of the kernel: nothing to do for one variant on the host
+static inline void pipeline_point(Pipe &) {}
 static inline u8 call_genotype(double p0, double p1, double p2) {
     double big = -1.0; int arg = -1;
     if (big < p0) { big = p0; arg = 0; }
@@ -42,8 +44,9 @@ def build_host_peel(tmp_path, src: str, S: int):
     args = ", ".join(f"lk[{c * 3 + g}]" for c in range(S) for g in range(3))
     wrapper = f"""
 extern "C" int peel_host(int chrx, const double *lk, const double *pa, const double *pm, double *row, u8 *gt_row) {{
-    return chrx ? peel_x(row, gt_row, pa[0], pa[1], pa[2], pm[0], pm[1], pm[2], {args})
-                : peel_a(row, gt_row, pa[0], pa[1], pa[2], pm[0], pm[1], pm[2], {args});
+    Pipe pipe;
+    return chrx ? peel_x(pipe, true, row, gt_row, pa[0], pa[1], pa[2], pm[0], pm[1], pm[2], {args})
+                : peel_a(pipe, true, row, gt_row, pa[0], pa[1], pa[2], pm[0], pm[1], pm[2], {args});
 }}
 """
     cpp, so = str(tmp_path / "peel.cpp"), str(tmp_path / "peel.so")

@@ -149,6 +149,38 @@ def test_es_generated_kernel_returns_the_same_doubles(pedname, cols, V, monkeypa
     assert np.array_equal(got.status, want["status"]) and np.array_equal(got.post[ok], want["post"][ok])
 
 
+@pytest.mark.parametrize("V", [4096 + 17, 29])
+def test_es_generated_kernel_when_a_row_sum_vanishes_inside_the_pedigree(V, monkeypatch):
+    """-mRate 0 and Mendel-impossible certain genotypes: the individual-only posteriors are fine, the peeling hits a zero sum
+    (family.cpp:1376-1384) and the variant fails AFTER the generated kernel has sent its `single` rows off -- the late clean-up
+    of es_jit.cu, in full tiles and in the ragged one.  Same bytes as the interpreter and the oracle."""
+    ped = synth.ped14()
+    cols = ped.sequenced_cols()
+    lk, fl = synth.synth_likelihoods(ped, V, seed=77, x_fraction=0.25)
+    kid = next(i for i in range(ped.n) if ped.mids[i] != 0)
+    mother, father = list(ped.ids).index(ped.mids[kid]), list(ped.ids).index(ped.fids[kid])
+    bad = np.arange(V) % 5 == 3
+    lk[np.ix_(bad, [mother, father])] = np.array([1.0, 0.0, 0.0])
+    lk[bad, kid] = np.array([0.0, 0.0, 1.0])
+    prm = fs.Params.default()
+    prm.mrate = 0.0
+    want = O.run(ped, cols, lk, fl, method=O.ES, mrate=0.0)
+    assert want["status"][bad].all() and not want["status"][~bad].all()
+    out = {}
+    for jit in ("0", "1"):
+        monkeypatch.setenv("FAMSEQ_ES_JIT", jit)
+        with engine_for(ped, cols, prm) as e:
+            out[jit] = e.run(fs.ES, lk, fl)
+            assert (e.info()["jit_launches"] >= 1) == (jit == "1")
+    for jit, got in out.items():
+        assert np.array_equal(got.status, want["status"]), jit
+        assert not got.post[got.status != 0].any() and not got.single[got.status != 0].any(), jit
+        assert (got.gt[got.status != 0] == 255).all(), jit
+        ok = want["status"] == 0
+        assert np.array_equal(got.post[ok], want["post"][ok]) and np.array_equal(got.single[ok], want["single"][ok]), jit
+    assert np.array_equal(out["0"].post, out["1"].post) and np.array_equal(out["0"].single, out["1"].single)
+
+
 def test_partial_sequencing_and_column_order():
     """Input columns in a different order than the ped rows, some members unsequenced."""
     ped = synth.ped14()
