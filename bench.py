@@ -467,7 +467,7 @@ def main():
     ap.add_argument("--variants", type=int, default=10_000_000, help="ES trio variants per GPU")
     ap.add_argument("--bn-variants", type=int, default=1_000_000)
     ap.add_argument("--mcmc-variants", type=int, default=1_000_000)
-    ap.add_argument("--es14-variants", type=int, default=1_000_000)
+    ap.add_argument("--es14-variants", type=int, default=4_000_000)
     ap.add_argument("--cli-variants", type=int, default=2_000_000)
     ap.add_argument("--methods", default="es,es14,bn,mcmc,cli,refgpu", help="which lines to time (es is the headline)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

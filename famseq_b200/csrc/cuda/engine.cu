@@ -323,6 +323,8 @@ int fs_create(const fs_pedigree *ped, const fs_params *params, int device, fs_en
             e->is_nuclear = true;
             np.allow_ident = 1;
             if (const char *env = std::getenv("FAMSEQ_ES_IDENT")) np.allow_ident = env[0] != '0';
+            np.stream_tiles = 0;
+            if (const char *env = std::getenv("FAMSEQ_ES_STREAM")) np.stream_tiles = std::max(-1, std::min(1 << 20, std::atoi(env)));
         }
         const char *env = std::getenv("FAMSEQ_ES_GENERIC");
         e->force_generic_es = env && env[0] == '1';

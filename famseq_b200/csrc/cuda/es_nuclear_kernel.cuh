@@ -65,6 +65,8 @@ __device__ __forceinline__ void bulk_commit_and_wait_read() {
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 template <bool X> __device__ __forceinline__ double trans(const RunConstants &C, int sel, int g, int a, int b) {
@@ -452,6 +454,120 @@ __global__ void __launch_bounds__(TB, MINB > 0 ? MINB : 1) es_nuclear_kernel(con
     }
 }
 
+// The same computation for compact input as a tile pipeline: a block walks a short list of consecutive tiles.  The compact tile
+// is small (192 S bytes + 32 flags), so it is double-buffered: tile k+1's TMA copy is issued when tile k starts and lands under
+// its arithmetic; the stores of tile k are committed and left alone, and only waited for (the copy engine's READ of shared
+// memory) right before tile k+1 writes the same rows.  With compact input the kernel is bound by instruction issue and
+// latencies, not HBM: with one tile per block a warp spent 20 % of its life waiting for its 576 bytes to arrive
+// (profiles/r2i_es_l3_sass.csv.gz: the mbarrier loop).
+template <int NC, bool SINGLE, bool IDENT, int MINB>
+__global__ void __launch_bounds__(32, MINB > 0 ? MINB : 1) es_nuclear_stream_kernel(const __grid_constant__ NuclearParams P, const BatchPtrs B, const int list_len) {
+    constexpr int TB = 32;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const RunConstants &C = P.C;
+    const int S = IDENT ? NC + 2 : C.s, S3 = 3 * S;
+    const unsigned out_bytes = (unsigned)(TB * S3 * sizeof(double));
+    const unsigned in_bytes = (unsigned)(TB * S3 * sizeof(uint16_t)), in_stride = (in_bytes + 15u) & ~15u;
+    double *s_post = reinterpret_cast<double *>(smem_raw); // [TB][S][3]
+    double *s_single = s_post + (SINGLE ? TB * S3 : 0);
+    unsigned char *s_in2 = reinterpret_cast<unsigned char *>(s_single + TB * S3); // [2][TB][S][3] uint16
+    uint8_t *s_gt = s_in2 + 2 * in_stride;                                         // [TB][S]
+    uint8_t *s_status = s_gt + ((TB * S + 15) & ~15);                              // [TB]
+    uint8_t *s_flags2 = s_status + TB;                                             // [2][TB]: the flags travel with their tile
+    __shared__ uint64_t bar;
+
+    const int lane = threadIdx.x;
+    const int64_t n_tiles = (B.V + TB - 1) / TB, n_full = B.V / TB;
+    int64_t tile = (int64_t)blockIdx.x * list_len; // this block's tiles: list_len consecutive ones
+    const int64_t list_end = min(n_tiles, tile + list_len);
+    if (tile >= list_end) return;
+    const unsigned tx_bytes = in_bytes + (B.flags ? (unsigned)TB : 0u);
+    auto fetch = [&](int64_t t, unsigned buf) { // lane 0: tile t into buffer buf
+        mbar_expect_tx(&bar, tx_bytes);
+        bulk_load(s_in2 + buf * in_stride, B.pl + t * TB * S3, in_bytes, &bar);
+        if (B.flags) bulk_load(s_flags2 + buf * TB, B.flags + t * TB, (unsigned)TB, &bar);
+    };
+    if (lane == 0) {
+        mbar_init(&bar, 1);
+        if (tile < n_full) fetch(tile, 0);
+    }
+    __syncwarp();
+    unsigned phase = 0, it = 0;
+    for (; tile < list_end; tile++, it ^= 1u) {
+        const int64_t v0 = tile * TB, next = tile + 1;
+        const int nv = (int)min((int64_t)TB, B.V - v0);
+        const bool full = nv == TB;
+        uint16_t *s_in = reinterpret_cast<uint16_t *>(s_in2 + it * in_stride);
+        uint8_t *s_flags = s_flags2 + it * TB;
+        if (full) {
+            mbar_wait(&bar, phase); // issued a tile ago
+            phase ^= 1u;
+        } else {
+            for (int k = lane; k < nv * S3; k += TB) s_in[k] = B.pl[v0 * S3 + k];
+            if (B.flags && lane < nv) s_flags[lane] = B.flags[v0 + lane];
+        }
+        // the next tile into the other buffer (its last readers finished a tile ago, and fenced); one copy in flight per barrier phase
+        if (lane == 0 && next < list_end && next < n_full) fetch(next, it ^ 1u);
+        if (lane == 0) bulk_wait_read(); // the previous tile's rows have left shared memory
+        __syncwarp();
+        // (a flag kept in a register across tiles gets spilled under the 72-register budget, and the spill waits for the load:
+        // 17 % of the kernel, profiles/r2s_es_l3_sass.csv.gz -- so the flags ride on the tile's TMA transaction)
+        const unsigned flag = (B.flags && lane < nv) ? s_flags[lane] : 0u;
+
+        if (lane < nv)
+            variant_thread<NC, true, SINGLE, IDENT>(P, flag, s_in + lane * S3, B.lut, s_post + lane * S3, s_single + lane * S3, s_gt + lane * S, s_status + lane);
+
+        if (full) {
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                bulk_store(B.post + v0 * S3, s_post, out_bytes);
+                if (SINGLE) bulk_store(B.single + v0 * S3, s_single, out_bytes);
+                bulk_store(B.gt + v0 * S, s_gt, (unsigned)(TB * S));
+                bulk_store(B.status + v0, s_status, (unsigned)TB);
+                bulk_commit();
+            }
+        } else {
+            __syncwarp();
+            for (int k = lane; k < nv * S3; k += TB) {
+                B.post[v0 * S3 + k] = s_post[k];
+                if (SINGLE) B.single[v0 * S3 + k] = s_single[k];
+            }
+            for (int k = lane; k < nv * S; k += TB) B.gt[v0 * S + k] = s_gt[k];
+            if (lane < nv) B.status[v0 + lane] = s_status[lane];
+        }
+    }
+    if (lane == 0) bulk_wait_read(); // shared memory must stay alive until the engine has read it
+}
+
+template <int NC, bool SINGLE, bool IDENT, int MINB>
+cudaError_t launch_stream(const NuclearParams &P, const BatchPtrs &B, cudaStream_t stream) {
+    constexpr int TB = 32;
+    const size_t S = (size_t)P.C.s;
+    const size_t in_bytes = (TB * S * 3 * sizeof(uint16_t) + 15) & ~(size_t)15;
+    const size_t smem = (SINGLE ? 2 : 1) * TB * S * 3 * sizeof(double) + 2 * in_bytes + ((TB * S + 15) & ~(size_t)15) + 3 * TB;
+    auto kernel = es_nuclear_stream_kernel<NC, SINGLE, IDENT, MINB>;
+    cudaError_t rc = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (rc != cudaSuccess) return rc;
+    int device = 0, n_sm = 0, per_sm = 0; // the grid: every block the device can hold at once
+    if ((rc = cudaGetDevice(&device)) != cudaSuccess) return rc;
+    if ((rc = cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device)) != cudaSuccess) return rc;
+    if ((rc = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TB, smem)) != cudaSuccess) return rc;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    // A block takes a SHORT list of consecutive tiles, not its share of the whole batch.  Measured on 10 M trio variants
+    // (profiles/r2u_stream.log, r2v_stream.log; fraction of the 167-byte roofline): 1 tile per block 0.805, 2 or 4 tiles 0.865,
+    // 8 tiles 0.82, 16 tiles 0.79, one list per resident block 0.67 -- with equal shares the blocks of the slower SMs finish
+    // last on their own (16 % of the warp slots empty over the run, profiles/r2s_r2s_es_l3.txt), so the balancing stays with the
+    // block scheduler and the lists only have to be long enough to halve the block launches and keep a copy in flight.  Larger
+    // sibships are less bandwidth-bound and like 8 (quads 0.72 -> 0.82, three children 0.67 -> 0.75).  Small batches get shorter
+    // lists, down to the one-tile-per-block arrangement.
+    const int64_t n_tiles = (B.V + TB - 1) / TB, resident = (int64_t)n_sm * per_sm;
+    const int list_len = (int)std::max<int64_t>(1, std::min<int64_t>(P.stream_tiles > 0 ? P.stream_tiles : (NC == 1 ? 4 : 8), n_tiles / (2 * resident)));
+    const unsigned grid = (unsigned)((n_tiles + list_len - 1) / list_len);
+    kernel<<<grid, TB, smem, stream>>>(P, B, list_len);
+    return cudaGetLastError();
+}
+
 template <int NC, int TB, bool PL, bool SINGLE, bool IDENT, int MINB>
 cudaError_t launch_minb(const NuclearParams &P, const BatchPtrs &B, cudaStream_t stream) {
     const size_t S = (size_t)P.C.s;
@@ -470,6 +586,8 @@ cudaError_t launch_minb(const NuclearParams &P, const BatchPtrs &B, cudaStream_t
 // children 0.75 -> 0.80 with 12 blocks; five children keep the compiler's choice (248 registers, 0.78; 10 blocks spill: 0.56).
 template <int NC, int TB, bool PL, bool SINGLE, bool IDENT> cudaError_t launch_ident(const NuclearParams &P, const BatchPtrs &B, cudaStream_t stream) {
     constexpr int kMinBlocks = NC == 1 ? 896 / TB : (NC == 2 ? 16 : (NC <= 4 ? 12 : 0));
+    // (the flags ride on the tile's TMA transaction: 16-byte alignment, like every other array)
+    if (PL && TB == 32 && P.stream_tiles >= 0 && (reinterpret_cast<uintptr_t>(B.flags) & 15u) == 0) return launch_stream<NC, SINGLE, IDENT, kMinBlocks>(P, B, stream);
     return launch_minb<NC, TB, PL, SINGLE, IDENT, kMinBlocks>(P, B, stream);
 }
 

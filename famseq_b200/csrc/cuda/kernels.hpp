@@ -32,6 +32,7 @@ struct NuclearParams {
     int32_t col_child[ES_NUCLEAR_MAX_CHILDREN];   // children in ped order
     int32_t male_child[ES_NUCLEAR_MAX_CHILDREN];
     int32_t allow_ident; // use the kernel specialised for the identity column map when it applies (FAMSEQ_ES_IDENT=0 turns it off)
+    int32_t stream_tiles; // compact input: tiles per block, each prefetched under the one before (0: 4 for trios, 8 otherwise; -1: the one-tile kernel; FAMSEQ_ES_STREAM)
 };
 // Handles B.pl (compact input, decoded through B.lut) and B.single == nullptr itself.
 cudaError_t launch_es_nuclear(const NuclearParams &P, const BatchPtrs &B, cudaStream_t stream);

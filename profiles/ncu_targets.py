@@ -2,7 +2,7 @@
     python profiles/ncu_targets.py es      # es_nuclear_kernel<1,32,...>: canonical, compact_in, compact_in_no_single (10 M variants each)
     python profiles/ncu_targets.py bn      # bn_kernel on ped14 (20 000 variants)
     python profiles/ncu_targets.py mcmc    # famseq_gibbs on ped40, 1 000 + 10 000 sweeps (37 888 variants = one wave)
-    python profiles/ncu_targets.py es14    # famseq_es on ped14 (1 M variants)
+    python profiles/ncu_targets.py es14    # famseq_es on ped14 (4 M variants)
 Run under `ncu -k regex:<kernel> ...` (profiles/ncu_capture_r2.sh); numbers printed by this script are not bench values."""
 import os
 import sys
@@ -45,4 +45,4 @@ elif what == "mcmc":
     run(synth.ped40(), fs.MCMC, 37_888, False, True, 1000, 10000)
 elif what == "es14":
     os.environ["FAMSEQ_ES_JIT"] = "1"
-    run(synth.ped14(), fs.ES, 1_000_000, False, True)
+    run(synth.ped14(), fs.ES, 4_000_000, False, True)

@@ -1,0 +1,15 @@
+#!/bin/bash
+# streaming nuclear kernel: tiles per block
+mkdir -p gpurun_out
+{
+for t in 0 2 4 8 16 32 1000; do
+  echo "tiles per block $t"
+  FAMSEQ_ES_STREAM=$t python profiles/es_time.py nuclear 1 10000000 compact
+  FAMSEQ_ES_STREAM=$t python profiles/es_time.py nuclear 1 10000000 compact_no_single
+done
+for t in 4 8 16; do
+  FAMSEQ_ES_STREAM=$t python profiles/es_time.py nuclear 2 10000000 compact
+  FAMSEQ_ES_STREAM=$t python profiles/es_time.py nuclear 3 10000000 compact
+done
+} > gpurun_out/r2u_stream.log 2>&1
+cat gpurun_out/r2u_stream.log | cut -c 1-160

@@ -176,6 +176,49 @@ def test_compact_input_on_device_buffers():
             assert np.array_equal(d_post.cpu().numpy(), host.post, equal_nan=True)
 
 
+@pytest.mark.parametrize("n_children,stream", [(1, None), (1, "5"), (1, "-1"), (2, None), (3, "3")])
+def test_tile_lists_of_the_compact_nuclear_kernel(n_children, stream, monkeypatch):
+    """A device-resident batch large enough for the nuclear kernel to give every block a LIST of tiles (es_nuclear_kernel.cuh,
+    es_nuclear_stream_kernel: double-buffered TMA input, stores left in flight): list lengths 4 / 8 (defaults), 5 and 3 (list
+    ends that are no multiple of anything), the one-tile kernel, a ragged last tile, chrX / Known flags and failing variants,
+    with and without `single`, a flags array that is not 16-byte aligned (the one-tile kernel takes that) -- the oracle's bytes."""
+    torch = pytest.importorskip("torch")
+    if stream is not None:
+        monkeypatch.setenv("FAMSEQ_ES_STREAM", stream)
+    rows = [(1, 0, 0, 1), (2, 0, 0, 2)] + [(3 + k, 2, 1, 1 + k % 2) for k in range(n_children)]
+    ped = synth._mk(rows)
+    V = 1_500_013
+    pl, fl = pl_batch(ped, V, seed=60 + n_children, x_fraction=0.3)
+    S = pl.shape[1]
+    want = O.run(ped, ped.sequenced_cols(), O.pl_table()[pl], fl, method=O.ES)
+    ok = want["status"] == 0
+    assert 0 < (~ok).sum() < V // 10
+    d_pl = torch.from_numpy(pl.view(np.int16)).cuda()
+    d_fl_padded = torch.zeros(V + 16, dtype=torch.uint8, device="cuda")
+    d_post = torch.empty((V, S, 3), dtype=torch.float64, device="cuda")
+    d_single = torch.empty_like(d_post)
+    d_gt = torch.empty((V, S), dtype=torch.uint8, device="cuda")
+    d_st = torch.empty(V, dtype=torch.uint8, device="cuda")
+    stream_h = torch.cuda.current_stream().cuda_stream
+    with engine_for(ped) as e:
+        for flag_offset, single in ((0, True), (0, False), (1, True)):
+            d_fl = d_fl_padded[flag_offset:flag_offset + V]
+            d_fl.copy_(torch.from_numpy(fl))
+            assert d_fl.data_ptr() % 16 == flag_offset
+            d_post.fill_(-1.0), d_single.fill_(-1.0), d_gt.fill_(77), d_st.fill_(77)
+            e.run_pl_device(fs.ES, V, d_pl.data_ptr(), d_fl.data_ptr(), d_post.data_ptr(), d_single.data_ptr() if single else None, d_gt.data_ptr(),
+                            d_st.data_ptr(), stream=stream_h)
+            torch.cuda.synchronize()
+            what = f"C={n_children} stream={stream} flags+{flag_offset} single={single}"
+            assert np.array_equal(d_st.cpu().numpy(), want["status"]), what
+            assert np.array_equal(d_post.cpu().numpy()[ok], want["post"][ok]), what
+            assert np.array_equal(d_gt.cpu().numpy()[ok], want["gt"][ok].astype(np.uint8)), what
+            assert not d_post.cpu().numpy()[~ok].any() and (d_gt.cpu().numpy()[~ok] == 255).all(), what
+            if single:
+                assert np.array_equal(d_single.cpu().numpy()[ok], want["single"][ok]), what
+                assert not d_single.cpu().numpy()[~ok].any(), what
+
+
 # ---- one engine over several GPUs (fs_create_multi) ---------------------------------------------------------
 def _multi_devices():
     n = fs.device_count()
