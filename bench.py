@@ -549,13 +549,13 @@ def main():
             ab = algorithmic_bytes(3, True, single)
             ach = ab * args.variants / (ms_c * 1e-3) / 1e9
             traffic = profile_json("es_trio_traffic.json").get(tag, {}).get("dram_bytes_per_variant")
-            layouts[tag] = {"kernel": "es_nuclear_kernel<1,32,true,%s,true> (uint16 PL tile in, decode-table gather, identity column map)" % ("true" if single else "false"),
+            layouts[tag] = {"kernel": "es_nuclear_stream_kernel<1,%s,true> (uint16 PL tiles in, 4 per block, each prefetched by TMA under the one before; decode-table gather, identity column map)" % ("true" if single else "false"),
                             "value": world * args.variants / (ms_c * 1e-3), "unit": UNIT, "ms_per_step": ms_c, "gpu_launches": l_c,
                             "failed_variants": f_c, "same_bytes_as_canonical": bool(torch.equal(keep["d_post"], want_post) and torch.equal(keep["d_gt"], want_gt)),
                             "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                                          "traffic": traffic * args.variants if traffic else None, "algorithmic_bytes_per_variant": ab,
-                                         "note": "these two layouts are bound by instruction issue / the FP64 pipe (~690 / ~610 instructions per variant, "
-                                                 "325 of them FP64: the FP64 pipe alone needs 0.13 ms per 10 M variants), not by HBM"}}
+                                         "note": "these two layouts are bound by instruction issue / the FP64 pipe (~740 / ~650 instructions per variant, 325 of "
+                                                 "them FP64; issue slots 72-74 % busy, FP64 pipe 58 %, profiles/r2x_r2x_es_l3.txt, _l5.txt), not by HBM"}}
         # headline e2e: the compact entry on pinned host buffers (2 B per likelihood up, post + gt + status down)
         e2e_s, h2d, d2h, same = time_e2e_path(torch, dist, eng, wl, rank, world, e2e_steps, args.warmup, keep, compact=True, single=False)
         # ... and with the posteriors as the reference prints them (Phred, six digits), 4 bytes per value

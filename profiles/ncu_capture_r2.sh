@@ -15,7 +15,7 @@ summarise() { # report -> gpurun_out/<name>.txt (+ the SASS page with per-instru
 }
 for what in "$@"; do
   case $what in
-    es)   k=es_nuclear_kernel;;
+    es)   k=es_nuclear;;   # es_nuclear_kernel (FP64 input) and es_nuclear_stream_kernel (compact input)
     bn)   k=bn_kernel;;
     mcmc) k=famseq_gibbs;;
     es14) k=famseq_es;;
