@@ -30,6 +30,7 @@ struct RunStats {
     long long phred_fixes = 0;     // values of those the device left to the host formatter
     double parse_s = 0, engine_s = 0, kernel_ms = 0, write_s = 0, total_s = 0;
     double read_s = 0, start_wait_s = 0, drain_s = 0; // input file read, waiting for fs_create, waiting for the writer
+    double alloc_s = 0, first_engine_s = 0;           // parts of engine_s: pinned buffers, the whole first block (first-use costs)
 };
 extern RunStats g_stats;
 
