@@ -89,9 +89,14 @@ __device__ __forceinline__ bool safe_dividend(double x) {
     const unsigned hi = (unsigned)__double2hiint(x) & 0x7fffffffu, lo = (unsigned)__double2loint(x);
     return (hi - ((1023u - 900u) << 20)) <= (1800u << 20) || (hi | lo) == 0u;
 }
-__device__ __forceinline__ void div3(double x0, double x1, double x2, double s, double &q0, double &q1, double &q2) {
-    const bool fast = ((unsigned)__double2hiint(s) - ((1023u - 900u) << 20)) <= (1800u << 20) & safe_dividend(x0) & safe_dividend(x1) &
-                      safe_dividend(x2);
+// `care`: this lane's quotients will be used (a lane that has failed, or only keeps the others company through the pedigree,
+// must not send the whole warp down the complete path).  The warp decides together -- all 32 lanes are here together by
+// construction: a uniform branch needs no divergence bookkeeping, and the complete division is right for every lane
+// whenever one lane needs it.
+__device__ __forceinline__ void div3(double x0, double x1, double x2, double s, double &q0, double &q1, double &q2, bool care) {
+    const bool in_range = ((unsigned)__double2hiint(s) - ((1023u - 900u) << 20)) <= (1800u << 20) & safe_dividend(x0) & safe_dividend(x1) &
+                          safe_dividend(x2);
+    const bool fast = __all_sync(0xffffffffu, in_range | !care);
     if (fast) {
         const double r = __drcp_rn(s);
         const double a = __dmul_rn(x0, r), b = __dmul_rn(x1, r), c = __dmul_rn(x2, r);
@@ -106,7 +111,7 @@ __device__ __forceinline__ void div3(double x0, double x1, double x2, double s, 
 }
 __device__ __forceinline__ bool lrc_wants_pedigree(double lrc, double l0, double l1, double l2, double big, double ls) {
     const bool no_negative = (__double2hiint(l0) | __double2hiint(l1) | __double2hiint(l2)) >= 0;
-    if (lrc == 1.0 && no_negative) return big < ls;
+    if (lrc == 1.0 && __all_sync(0xffffffffu, no_negative)) return big < ls;
     return __ddiv_rn(big, ls) < lrc;
 }
 __device__ __forceinline__ u8 call_genotype(double p0, double p1, double p2) {
@@ -246,7 +251,7 @@ class Emitter {
                     const int col = (int)(w0 >> 9);
                     if (!point_emitted_) o_ << "    pipeline_point(pipe);\n";
                     point_emitted_ = true;
-                    o_ << "    { double q0, q1, q2; div3(" << t << "m0, " << t << "m1, " << t << "m2, " << t << "sum, q0, q1, q2);\n"
+                    o_ << "    { double q0, q1, q2; div3(" << t << "m0, " << t << "m1, " << t << "m2, " << t << "sum, q0, q1, q2, mine);\n"
                        << "      if (mine) { row[" << col * 3 << "] = q0; row[" << col * 3 + 1 << "] = q1; row[" << col * 3 + 2 << "] = q2; gt_row[" << col
                        << "] = call_genotype(q0, q1, q2); } }\n";
                 }
@@ -370,7 +375,7 @@ std::string es_jit_source(const EsParams &P) {
           << "        const double r0 = __dmul_rn(L" << c << "_0, " << pr << "0), r1 = __dmul_rn(L" << c << "_1, " << pr << "1), r2 = __dmul_rn(L" << c << "_2, " << pr << "2);\n"
           << "        const double rs = __dadd_rn(__dadd_rn(r0, r1), r2);\n"
           << "        if (rs <= 0.0) failed = true;\n"
-          << "        double q0, q1, q2; div3(r0, r1, r2, rs, q0, q1, q2);\n"
+          << "        double q0, q1, q2; div3(r0, r1, r2, rs, q0, q1, q2, !(rs <= 0.0));\n"
           << "        single_row[" << c * 3 << "] = q0; single_row[" << c * 3 + 1 << "] = q1; single_row[" << c * 3 + 2 << "] = q2;\n"
           << "        gt_row[" << c << "] = call_genotype(q0, q1, q2);\n"
           << "        double big = 0.0;\n"

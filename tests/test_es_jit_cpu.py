@@ -25,7 +25,7 @@ typedef unsigned int u32; typedef unsigned long long u64; typedef long long i64;
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
 static inline double __longlong_as_double(long long x) { double d; std::memcpy(&d, &x, 8); return d; }
-static inline void div3(double x0, double x1, double x2, double s, double &q0, double &q1, double &q2) { q0 = x0 / s; q1 = x1 / s; q2 = x2 / s; }
+static inline void div3(double x0, double x1, double x2, double s, double &q0, double &q1, double &q2, bool) { q0 = x0 / s; q1 = x1 / s; q2 = x2 / s; }
 struct Pipe {};                                   // the tile pipeline of the kernel: nothing to do for one variant on the host
 static inline void pipeline_point(Pipe &) {}
 static inline u8 call_genotype(double p0, double p1, double p2) {
