@@ -506,6 +506,10 @@ __global__ void __launch_bounds__(32, MINB > 0 ? MINB : 1) es_nuclear_stream_ker
             for (int k = lane; k < nv * S3; k += TB) s_in[k] = B.pl[v0 * S3 + k];
             if (B.flags && lane < nv) s_flags[lane] = B.flags[v0 + lane];
         }
+        // Every lane has seen this tile's phase complete before the barrier is armed again: a lane still in front of the wait
+        // when the NEXT phase completes would be waiting for the one after it (tests/test_nuclear_stream_cpu.py runs the
+        // lanes as free-running threads and hangs without this).
+        __syncwarp();
         // the next tile into the other buffer (its last readers finished a tile ago, and fenced); one copy in flight per barrier phase
         if (lane == 0 && next < list_end && next < n_full) fetch(next, it ^ 1u);
         if (lane == 0) bulk_wait_read(); // the previous tile's rows have left shared memory

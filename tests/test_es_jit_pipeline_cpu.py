@@ -106,7 +106,7 @@ static inline void mbar_wait(u64 *, unsigned parity) {
     long spins = 0;
     while ((g_phases_done.load() & 1u) == parity) {
         std::this_thread::yield();
-        if (++spins > 200000000L) { std::fprintf(stderr, "shim: mbarrier wait never ends\n"); std::_Exit(3); }
+        if (++spins > 20000000L) { std::fprintf(stderr, "shim: mbarrier wait never ends\n"); std::_Exit(3); }
     }
 }
 static inline void bulk_store(void *gmem_dst, const void *smem_src, unsigned bytes) {
