@@ -6,7 +6,7 @@ launch functions are cut out of the text, a stand-in <cuda_runtime.h> supplies t
 shim plays the rest: a warp is 32 host threads (`__syncwarp` = a barrier), the device intrinsics are plain double operations
 (-ffp-contract=off), and the copy engine is an adversary as in test_es_jit_pipeline_cpu.py -- a bulk load lands at the earliest
 legal moment and a bulk store reads shared memory at the latest one (inside the wait_group that follows it), or the other way
-round.  Blocks walk lists of 1, 3 and 4 consecutive tiles (double-buffered compact tiles, flags on the tile's transaction, output
+round.  The one-tile kernel runs on FP64 and on compact input; blocks of the tile-list kernel walk 1, 3, 4 and 11 consecutive tiles (double-buffered compact tiles, flags on the tile's transaction, output
 rows reused from tile to tile), the last tile is ragged; the results must be the oracle's bytes on the decoded likelihoods,
 with and without `single`, without flags, for trios and quads.  Where the tool chain has ThreadSanitizer the program also runs
 under it.  Test infrastructure: the product has no CPU compute path."""
@@ -159,8 +159,10 @@ static int run_grid(const NuclearParams &P, const BatchPtrs &B, int list_len) {
                 threadIdx.x = (unsigned)l;
                 if (list_len > 0)
                     es_nuclear_stream_kernel<NC, SINGLE, true, 0>(P, B, list_len);
-                else // the one-tile kernel on the same input
+                else if (B.pl) // the one-tile kernel on the same input
                     es_nuclear_kernel<NC, 32, true, SINGLE, true, 0>(P, B);
+                else // ... and on FP64 likelihoods, general column map: the headline kernel
+                    es_nuclear_kernel<NC, 32, false, SINGLE, false, 0>(P, B);
             });
         for (auto &t : lanes) t.join();
         if (!g_open_stores.empty() || !g_committed_stores.empty()) {
@@ -219,6 +221,11 @@ int main(int argc, char **argv) {
     BatchPtrs B;
     B.lk = nullptr, B.flags = use_flags ? flags : nullptr, B.post = post, B.single = want_single ? single : nullptr, B.gt = gt, B.status = status, B.V = V;
     B.pl = pl, B.lut = lut;
+    if (list_len < 0) { // FP64 input: the decoded likelihoods
+        double *lk = (double *)room(n3 * 8);
+        for (size_t k = 0; k < n3; k++) lk[k] = lut[pl[k]];
+        B.lk = lk, B.pl = nullptr, B.lut = nullptr;
+    }
     int errors = 0;
     if (nc == 1) errors = want_single ? run_grid<1, true>(P, B, list_len) : run_grid<1, false>(P, B, list_len);
     else if (nc == 2) errors = want_single ? run_grid<2, true>(P, B, list_len) : run_grid<2, false>(P, B, list_len);
@@ -323,7 +330,7 @@ def test_tile_lists_of_the_compact_nuclear_kernel_against_an_adversarial_copy_en
     assert 0 < (want["status"] != 0).sum() < V
     want_noflags = O.run(ped, ped.sequenced_cols(), O.pl_table()[pl], np.zeros_like(fl), method=O.ES)
     plain, tsan = build(tmp_path)
-    for list_len in (0, 1, 3, 4, 64):  # 0: the one-tile kernel; 64: one block walks everything
+    for list_len in (-1, 0, 1, 3, 4, 64):  # -1 / 0: the one-tile kernel on FP64 / compact input; 64: one block walks everything
         for late_loads, late_stores in ((0, 1), (1, 0)):
             for want_single in (True, False):
                 got = run(tmp_path, plain, ped, pl, fl, list_len, late_loads, late_stores, want_single)
