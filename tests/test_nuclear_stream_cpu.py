@@ -145,7 +145,7 @@ template <class T> static inline T __ldg(const T *p) { return *p; }
 DRIVER = r"""
 #include "../host/pedigree.hpp"
 namespace famseq {
-template <int NC, bool SINGLE>
+template <int NC, bool SINGLE, bool IDENT>
 static int run_grid(const NuclearParams &P, const BatchPtrs &B, int list_len) {
     const int64_t n_tiles = (B.V + 31) / 32;
     const int grid = list_len > 0 ? (int)((n_tiles + list_len - 1) / list_len) : (int)n_tiles;
@@ -158,11 +158,11 @@ static int run_grid(const NuclearParams &P, const BatchPtrs &B, int list_len) {
             lanes.emplace_back([&, l] {
                 threadIdx.x = (unsigned)l;
                 if (list_len > 0)
-                    es_nuclear_stream_kernel<NC, SINGLE, true, 0>(P, B, list_len);
+                    es_nuclear_stream_kernel<NC, SINGLE, IDENT, 0>(P, B, list_len);
                 else if (B.pl) // the one-tile kernel on the same input
-                    es_nuclear_kernel<NC, 32, true, SINGLE, true, 0>(P, B);
-                else // ... and on FP64 likelihoods, general column map: the headline kernel
-                    es_nuclear_kernel<NC, 32, false, SINGLE, false, 0>(P, B);
+                    es_nuclear_kernel<NC, 32, true, SINGLE, IDENT, 0>(P, B);
+                else // ... and on FP64 likelihoods
+                    es_nuclear_kernel<NC, 32, false, SINGLE, IDENT, 0>(P, B);
             });
         for (auto &t : lanes) t.join();
         if (!g_open_stores.empty() || !g_committed_stores.empty()) {
@@ -176,9 +176,14 @@ static int run_grid(const NuclearParams &P, const BatchPtrs &B, int list_len) {
     }
     return g_errors;
 }
+template <int NC> static int run_nc(const NuclearParams &P, const BatchPtrs &B, int list_len, bool ident) {
+    if (ident) return B.single ? run_grid<NC, true, true>(P, B, list_len) : run_grid<NC, false, true>(P, B, list_len);
+    return B.single ? run_grid<NC, true, false>(P, B, list_len) : run_grid<NC, false, false>(P, B, list_len);
+}
 }
 // usage: prog n_children list_len late_loads late_stores want_single use_flags V in.bin out.bin
-//   in : mrate, lrc, priors[4][3] (f64), male_child[5] (i32), lut[65536] (f64), pl [V][S][3] (u16), flags [V]
+//   in : mrate, lrc, priors[4][3] (f64); S, role_col[7] (father, mother, children; -1 = unsequenced), male_child[5] (i32);
+//        lut[65536] (f64), pl [V][S][3] (u16), flags [V]
 //   out: post [V][S][3], single [V][S][3] (f64), gt [V][S], status [V]
 int main(int argc, char **argv) {
     using namespace famseq;
@@ -188,30 +193,47 @@ int main(int argc, char **argv) {
     g_late_stores = std::atoi(argv[4]);
     const bool want_single = std::atoi(argv[5]) != 0, use_flags = std::atoi(argv[6]) != 0;
     const int64_t V = std::atoll(argv[7]);
-    const int S = nc + 2;
-    const size_t n3 = (size_t)V * S * 3, n1 = (size_t)V * S;
     auto room = [](size_t bytes) { return std::aligned_alloc(128, (bytes + 127) / 128 * 128 + 128); };
     FILE *f = std::fopen(argv[8], "rb");
     if (!f) return 2;
     double head[2 + 12];
-    int32_t male_child[5];
+    int32_t ints[1 + 7 + 5];
+    if (std::fread(head, 8, 14, f) != 14 || std::fread(ints, 4, 13, f) != 13) return 2;
+    const int S = ints[0];
+    const int32_t *role_col = ints + 1, *male_child = ints + 8;
+    const size_t n3 = (size_t)V * S * 3, n1 = (size_t)V * S;
     double *lut = (double *)room(65536 * 8);
     uint16_t *pl = (uint16_t *)room(n3 * 2);
     uint8_t *flags = (uint8_t *)room((size_t)V);
-    if (std::fread(head, 8, 14, f) != 14 || std::fread(male_child, 4, 5, f) != 5 || std::fread(lut, 8, 65536, f) != 65536 ||
-        std::fread(pl, 2, n3, f) != n3 || std::fread(flags, 1, (size_t)V, f) != (size_t)V)
-        return 2;
+    if (std::fread(lut, 8, 65536, f) != 65536 || std::fread(pl, 2, n3, f) != n3 || std::fread(flags, 1, (size_t)V, f) != (size_t)V) return 2;
     std::fclose(f);
     NuclearParams P;
     std::memset(&P, 0, sizeof P);
     build_tables(head[0], P.C.tab);
     P.C.lrc = head[1];
     std::memcpy(P.C.prior, head + 2, 96);
-    P.C.n = P.C.s = S;
-    P.C.col_male[0] = 1; // columns in role order: father, mother, children
+    P.C.n = nc + 2, P.C.s = S;
     P.n_children = nc;
-    P.col_father = 0, P.col_mother = 1;
-    for (int c = 0; c < nc; c++) P.col_child[c] = 2 + c, P.male_child[c] = male_child[c], P.C.col_male[2 + c] = (uint8_t)male_child[c];
+    P.col_father = role_col[0], P.col_mother = role_col[1];
+    if (role_col[0] >= 0) P.C.col_male[role_col[0]] = 1;
+    bool ident = S == nc + 2 && role_col[0] == 0 && role_col[1] == 1;
+    for (int c = 0; c < nc; c++) {
+        P.col_child[c] = role_col[2 + c], P.male_child[c] = male_child[c];
+        if (role_col[2 + c] >= 0) P.C.col_male[role_col[2 + c]] = (uint8_t)male_child[c];
+        ident = ident && role_col[2 + c] == 2 + c;
+    }
+    // unseq_fail (engine.cu: fs_create): an unsequenced member whose prior row sums to <= 0 fails every such variant
+    for (int fl = 0; fl < 4; fl++) {
+        const int known = fl & 1, chrx = (fl >> 1) & 1;
+        bool bad = false;
+        for (int r = 0; r < nc + 2; r++) {
+            if (role_col[r] >= 0) continue;
+            const bool male = r == 0 || (r >= 2 && male_child[r - 2]);
+            const double *pr = (chrx && male) ? P.C.prior[known ? 3 : 2] : P.C.prior[known ? 1 : 0];
+            if ((pr[0] + pr[1]) + pr[2] <= 0) bad = true;
+        }
+        P.C.unseq_fail[fl] = bad;
+    }
     P.allow_ident = 1;
     double *post = (double *)room(n3 * 8), *single = (double *)room(n3 * 8);
     uint8_t *gt = (uint8_t *)room(n1), *status = (uint8_t *)room((size_t)V);
@@ -226,9 +248,11 @@ int main(int argc, char **argv) {
         for (size_t k = 0; k < n3; k++) lk[k] = lut[pl[k]];
         B.lk = lk, B.pl = nullptr, B.lut = nullptr;
     }
+    ident = ident && (B.pl || nc > 1); // the product's rule (launch_io): the FP64 trio keeps the general code
     int errors = 0;
-    if (nc == 1) errors = want_single ? run_grid<1, true>(P, B, list_len) : run_grid<1, false>(P, B, list_len);
-    else if (nc == 2) errors = want_single ? run_grid<2, true>(P, B, list_len) : run_grid<2, false>(P, B, list_len);
+    if (nc == 1) errors = run_nc<1>(P, B, list_len, ident);
+    else if (nc == 2) errors = run_nc<2>(P, B, list_len, ident);
+    else if (nc == 3) errors = run_nc<3>(P, B, list_len, ident);
     else return 2;
     f = std::fopen(argv[9], "wb");
     if (!f) return 2;
@@ -256,7 +280,7 @@ def host_source() -> str:
     return text.replace("extern __shared__ __align__(128) unsigned char smem_raw[];", "").replace("#pragma once", "")
 
 
-def build(tmp_path, source=None):
+def build(tmp_path, source=None, with_tsan=True):
     inc = tmp_path / "inc"
     inc.mkdir(exist_ok=True)
     (inc / "cuda_runtime.h").write_text(FAKE_CUDA_RUNTIME)
@@ -265,23 +289,45 @@ def build(tmp_path, source=None):
     flags = ["-O1", "-std=c++20", "-ffp-contract=off", "-pthread", "-w", f"-I{inc}", f"-I{os.path.join(CSRC, 'cuda')}"]
     extra = [os.path.join(CSRC, "host", "pedigree.cpp")]
     plain, tsan = str(tmp_path / "nuclear_host"), str(tmp_path / "nuclear_host_tsan")
-    subprocess.run(["g++"] + flags + ["-o", plain, cpp] + extra, check=True)
-    if subprocess.run(["g++", "-fsanitize=thread", "-g"] + flags + ["-o", tsan, cpp] + extra, capture_output=True).returncode != 0:
-        tsan = None
-    return plain, tsan
+    jobs = [subprocess.Popen(["g++"] + flags + ["-o", plain, cpp] + extra)]
+    if with_tsan:
+        jobs.append(subprocess.Popen(["g++", "-fsanitize=thread", "-g"] + flags + ["-o", tsan, cpp] + extra, stderr=subprocess.DEVNULL))
+    rcs = [j.wait() for j in jobs]
+    assert rcs[0] == 0, "the kernel source does not compile for the host"
+    return plain, (tsan if with_tsan and rcs[1] == 0 else None)
 
 
-def run(tmp_path, prog, ped, pl, fl, list_len, late_loads, late_stores, want_single=True, use_flags=True):
+@pytest.fixture(scope="module")
+def programs(tmp_path_factory):
+    """The host programs of the unmodified kernel source, built once: (plain, under ThreadSanitizer or None)."""
+    return build(tmp_path_factory.mktemp("nuclear_host"))
+
+
+def roles_of(ped):
+    """Ped row of the father, the mother and the children (ped order) of a nuclear family."""
+    ids = list(ped.ids)
+    kids = [i for i in range(ped.n) if ped.mids[i] != 0]
+    return [ids.index(ped.fids[kids[0]]), ids.index(ped.mids[kids[0]])] + kids
+
+
+def run(tmp_path, prog, ped, pl, fl, list_len, late_loads, late_stores, want_single=True, use_flags=True, cols=None):
+    cols = list(ped.sequenced_cols() if cols is None else cols)
     V, S = pl.shape[0], pl.shape[1]
-    nc = S - 2
+    assert S == len(cols)
+    roles = roles_of(ped)
+    nc = len(roles) - 2
     prm = fs.Params.default()
-    male_child = np.zeros(5, np.int32)
-    male_child[:nc] = [1 if g == 1 else 0 for g in list(ped.genders)[2:]]
+    ints = np.full(13, -1, np.int32)
+    ints[0] = S
+    for r, row in enumerate(roles):
+        ints[1 + r] = cols.index(row) if row in cols else -1
+    ints[8:13] = 0
+    ints[8:8 + nc] = [1 if ped.genders[row] == 1 else 0 for row in roles[2:]]
     inp, out = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
     with open(inp, "wb") as f:
         f.write(np.array([prm.mrate, prm.lrc], np.float64).tobytes())
         f.write(np.ascontiguousarray(prm.priors(), np.float64).tobytes())
-        f.write(male_child.tobytes())
+        f.write(ints.tobytes())
         f.write(np.ascontiguousarray(O.pl_table(), np.float64).tobytes())
         f.write(np.ascontiguousarray(pl, np.uint16).tobytes())
         f.write(np.ascontiguousarray(fl, np.uint8).tobytes())
@@ -321,7 +367,7 @@ def batch(ped, V, seed):
 
 
 @pytest.mark.parametrize("n_children", [1, 2])
-def test_tile_lists_of_the_compact_nuclear_kernel_against_an_adversarial_copy_engine(n_children, tmp_path):
+def test_tile_lists_of_the_compact_nuclear_kernel_against_an_adversarial_copy_engine(n_children, tmp_path, programs):
     rows = [(1, 0, 0, 1), (2, 0, 0, 2)] + [(3 + k, 2, 1, 1 + k % 2) for k in range(n_children)]
     ped = synth._mk(rows)
     V = 32 * 10 + 7  # eleven tiles, the last one ragged
@@ -329,7 +375,7 @@ def test_tile_lists_of_the_compact_nuclear_kernel_against_an_adversarial_copy_en
     want = O.run(ped, ped.sequenced_cols(), O.pl_table()[pl], fl, method=O.ES)
     assert 0 < (want["status"] != 0).sum() < V
     want_noflags = O.run(ped, ped.sequenced_cols(), O.pl_table()[pl], np.zeros_like(fl), method=O.ES)
-    plain, tsan = build(tmp_path)
+    plain, tsan = programs
     for list_len in (-1, 0, 1, 3, 4, 64):  # -1 / 0: the one-tile kernel on FP64 / compact input; 64: one block walks everything
         for late_loads, late_stores in ((0, 1), (1, 0)):
             for want_single in (True, False):
@@ -342,6 +388,27 @@ def test_tile_lists_of_the_compact_nuclear_kernel_against_an_adversarial_copy_en
         check(got, want, True, "under ThreadSanitizer")
 
 
+@pytest.mark.parametrize("rows,cols", [
+    ([(7, 5, 9, 2), (9, 0, 0, 1), (4, 5, 9, 1), (5, 0, 0, 2)], [3, 0, 2]),          # children before parents, the father unsequenced
+    ([(1, 0, 0, 1), (2, 0, 0, 2), (3, 2, 1, 1), (4, 2, 1, 2), (5, 2, 1, 1)], None),   # three children, identity column map
+    ([(1, 0, 0, 1), (2, 0, 0, 2), (3, 2, 1, 2), (4, 2, 1, 1), (5, 2, 1, 2)], [4, 1, 0, 2]),  # three children, one unsequenced, columns permuted
+])
+def test_column_maps_of_the_nuclear_kernel_on_the_host(rows, cols, tmp_path, programs):
+    """The arithmetic of the nuclear kernel's source (fast pass, complete pass, both column-map code paths) against the oracle
+    on the host: unsequenced members, permuted columns, three children; FP64 and compact input, one tile and lists of tiles."""
+    ped = synth._mk(rows)
+    cols = ped.sequenced_cols() if cols is None else cols
+    V = 32 * 5 + 9
+    pl, fl = batch(synth._mk([(i, 0, 0, 1) for i in range(1, len(cols) + 1)]), V, seed=17 + len(cols))
+    want = O.run(ped, cols, O.pl_table()[pl], fl, method=O.ES)
+    assert 0 < (want["status"] != 0).sum() < V
+    plain, _ = programs
+    for list_len in (-1, 0, 3):
+        for want_single in (True, False):
+            got = run(tmp_path, plain, ped, pl, fl, list_len, 0, 1, want_single, cols=cols)
+            check(got, want, want_single, f"rows={rows} cols={cols} list={list_len} single={want_single}")
+
+
 def test_the_adversary_notices_a_missing_wait(tmp_path):
     """The shim must be able to fail: without the wait for the previous tile's stores, its rows are overwritten before the copy
     engine (reading as late as it may) has taken them."""
@@ -352,7 +419,7 @@ def test_the_adversary_notices_a_missing_wait(tmp_path):
     needle = "        if (lane == 0) bulk_wait_read(); // the previous tile's rows have left shared memory\n"
     text = host_source()
     assert text.count(needle) == 1
-    plain, _ = build(tmp_path, text.replace(needle, ""))
+    plain, _ = build(tmp_path, text.replace(needle, ""), with_tsan=False)
     post, single, gt, status = run(tmp_path, plain, ped, pl, fl, 4, 0, 1, True)
     ok = want["status"] == 0
     assert not np.array_equal(post[ok], want["post"][ok])
