@@ -121,7 +121,9 @@ int fs_run(fs_engine *e, int method, int64_t V, const double *lk, const uint8_t 
            uint8_t *status);
 
 /* Same computation on DEVICE buffers, enqueued on `stream` (a cudaStream_t, NULL = default stream) and
- * not synchronised: this is the kernel-only path that bench.py times with CUDA events. */
+ * not synchronised: this is the kernel-only path that bench.py times with CUDA events.  d_lk, d_post and d_single must be
+ * 16-byte aligned (FS_E_ARG otherwise; cudaMalloc'ed arrays are); the byte arrays (flags, gt, status, and pl below) may
+ * have any alignment -- 16-byte aligned ones take the kernels that move whole tiles with the copy engine. */
 int fs_run_device(fs_engine *e, int method, int64_t V, const double *d_lk, const uint8_t *d_flags, int32_t burn,
                   int32_t rep, uint64_t seed, int64_t v_offset, double *d_post, double *d_single,
                   uint8_t *d_gt, uint8_t *d_status, void *stream);
