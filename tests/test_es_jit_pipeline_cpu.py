@@ -234,10 +234,11 @@ def check(got, want, what):
     assert not post[~ok].any() and not single[~ok].any() and (gt[~ok] == 255).all(), what
 
 
-@pytest.mark.parametrize("name,mrate", [("half_sibs", 1e-7), ("ped14", 0.0)])
-def test_tile_pipeline_of_the_generated_kernel_against_an_adversarial_copy_engine(name, mrate, tmp_path):
+@pytest.mark.parametrize("name,mrate,cols", [("half_sibs", 1e-7, None), ("ped14", 0.0, None), ("three_wives", 1e-7, None),
+                                             ("ped14", 1e-7, [13, 2, 7, 0, 10, 5])])
+def test_tile_pipeline_of_the_generated_kernel_against_an_adversarial_copy_engine(name, mrate, cols, tmp_path):
     ped = synth.PEDIGREES[name]()
-    cols = ped.sequenced_cols()
+    cols = ped.sequenced_cols() if cols is None else cols
     S = len(cols)
     V = 32 * 9 + 13  # ten tiles, the last one ragged
     lk, fl = synth.synth_likelihoods(synth._mk([(i, 0, 0, 1) for i in range(1, S + 1)]), V, seed=2718, x_fraction=0.3)
